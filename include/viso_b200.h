@@ -1,0 +1,187 @@
+/*
+ * viso_b200.h -- C-ABI of the B200-native libviso hot path (libviso_b200/libviso_b200.so).
+ *
+ * The reference (alexkreimer/libviso) has no FFI: its boundary is the set of free C++ functions declared in
+ * src/viso.h, src/mvg.h and src/estimation.h and linked statically into `kitti` and `tester`
+ * (reference src/CMakeLists.txt:17-20).  Every entry point below replaces the body of one of those functions
+ * (file:line given per function); the C++ mirror of the reference headers that calls them lives in
+ * libviso_b200/host/ and INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes, no C++ / torch types; all matrices row-major like cv::Mat;
+ * every function returns VISO_OK (0) or a negative viso_status and never throws; text for the last error of a
+ * context is available through viso_last_error().  All host-buffer functions are synchronous.  There is NO CPU
+ * fallback: without a CUDA device viso_create() fails and nothing else can be called.
+ *
+ * Domain restrictions (checked on the device, VISO_ERR_DOMAIN when violated):
+ *   - descriptors must be integer valued with |v| <= 1023 and desc_len <= 128 (the reference's descriptors are
+ *     3x3 Sobel-x responses of 8-bit images, |v| <= 1020, 121 per keypoint: viso.cpp:999-1002,1010);
+ *   - 1 <= max_neighbors <= 1024.
+ */
+#ifndef VISO_B200_H_
+#define VISO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VISO_ABI_VERSION 1
+#define VISO_DESC_PAD 128 /* packed descriptor row: 128 x u16 = 256 B */
+
+typedef enum {
+    VISO_OK = 0,
+    VISO_ERR_CUDA = -1,        /* a CUDA runtime call failed; see viso_last_error */
+    VISO_ERR_ARG = -2,         /* bad argument (null pointer, negative size, ...) */
+    VISO_ERR_DOMAIN = -3,      /* input outside the supported domain (see above) */
+    VISO_ERR_DIV0 = -4,        /* h2e: homogeneous w == 0 (the reference throws std::overflow_error, misc.h:118-119) */
+    VISO_ERR_DUPLICATE = -5,   /* match_circle: a Matches list has a repeated query index (never produced by match_desc) */
+    VISO_ERR_NOMEM = -6
+} viso_status;
+
+/* MatchParams, reference src/viso.cpp:48-75 */
+typedef struct {
+    int32_t enforce_epipolar;
+    int32_t enforce_2nd_best;
+    int32_t max_neighbors;
+    int32_t _pad;
+    double radius;
+    double sampson_thresh;
+    double ratio_2nd_best;
+    double F[9];
+} viso_match_params;
+
+/* struct param, reference src/viso.h:58-72 (calib.f/cu/cv flattened) */
+typedef struct {
+    double base;
+    double f, cu, cv;
+    double inlier_threshold;
+    double thresh;
+    int32_t ransac_iter;
+    int32_t _pad;
+} viso_param;
+
+/* One frame pair's result: what sequence_odometry (viso.cpp:1313-1324) needs to chain poses. 64 bytes. */
+typedef struct {
+    double tr[6];
+    int32_t ok;         /* ransac_minimize_reproj returned true */
+    int32_t n_inliers;
+    int32_t n_circ;     /* circular matches; < 3 => frame skipped (viso.cpp:1283-1288) */
+    int32_t best_hyp;   /* winning hypothesis or -1 */
+} viso_record;
+
+typedef struct viso_ctx viso_ctx;
+typedef struct viso_seq viso_seq;
+
+int viso_abi_version(void);
+
+/* ---- context ---- */
+int viso_create(viso_ctx** ctx, int device);
+void viso_destroy(viso_ctx* ctx);
+const char* viso_last_error(const viso_ctx* ctx);
+void* viso_stream(viso_ctx* ctx);                  /* the cudaStream_t every kernel of this context is launched on */
+int viso_sync(viso_ctx* ctx);
+/* extent of the uniform candidate grid (pixels); coordinates outside are clamped into border cells, so any
+ * value is correct, a matching one is fast.  Default 1248 x 384. */
+int viso_set_image_extent(viso_ctx* ctx, int width, int height);
+/* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
+int64_t viso_launch_count(const viso_ctx* ctx);
+
+void viso_match_params_stereo(viso_match_params* p, const double F[9]); /* MatchParams(Mat F), viso.cpp:62-71 */
+void viso_match_params_temporal(viso_match_params* p);                  /* MatchParams(), viso.cpp:72-74 */
+void viso_param_default(viso_param* p);                                 /* param(), viso.h:60 */
+
+/* ---- match_desc, reference src/viso.cpp:668-726 (+ radiusSearch :170-203, sampsonDistance :652-666) ----
+ * kp: n x 2 float (x,y); d: n x desc_len float.  Dense per-query outputs (n1 each, host):
+ *   best_idx (-1: none), best_d1, best_d2 (INT32_MAX: none), valid (1 iff the reference pushes a Match).
+ * The caller compacts valid rows in query order into Match(i,best_idx,best_d1) and applies std::sort by dist
+ * (viso.cpp:724); libviso_b200/host/viso.cpp does exactly that. */
+int viso_match_desc(viso_ctx* ctx, const float* kp1, int n1, const float* kp2, int n2,
+                    const float* d1, const float* d2, int desc_len, const viso_match_params* params,
+                    int32_t* best_idx, int32_t* best_d1, int32_t* best_d2, int32_t* valid);
+/* same, plus the compaction and the reference's std::sort order done on the device (restated libstdc++
+ * introsort); matches: n1 x 3 ints capacity, n_matches out */
+int viso_match_desc_sorted(viso_ctx* ctx, const float* kp1, int n1, const float* kp2, int n2,
+                           const float* d1, const float* d2, int desc_len, const viso_match_params* params,
+                           int32_t* matches, int32_t* n_matches);
+
+/* ---- match_circle, reference src/viso.cpp:206-243.  Matches are m x 3 ints. circ4: cap nlr x 4, pcl3: cap nlr x 3 */
+int viso_match_circle(viso_ctx* ctx, const int32_t* match_lr, int nlr, const int32_t* match_lr_prev, int nlrp,
+                      const int32_t* match11, int n11, const int32_t* match22, int n22,
+                      int32_t* circ4, int32_t* pcl3, int32_t* n_out);
+
+/* ---- collect_matches (Mat x, 4 x m), reference src/viso.cpp:501-514, fused with
+ *      triangulate_rectified<double>, reference src/viso.cpp:1137-1162.  x: 4 x m, X: 3 x m (either may be NULL) */
+int viso_collect_triangulate(viso_ctx* ctx, const float* kp1, int n1, const float* kp2, int n2,
+                             const int32_t* matches, int m, double f, double base, double cu, double cv,
+                             double* x, double* X);
+/* triangulate_rectified<double>(x, ...), reference src/viso.cpp:1137-1154 */
+int viso_triangulate_rectified_f64(viso_ctx* ctx, const double* x, int m, double f, double base, double cu, double cv,
+                                   double* X);
+/* triangulate_rectified (float), reference src/mvg.cpp:172-192; x1,x2: 2 x m, X: 3 x m */
+int viso_triangulate_rectified_f32(viso_ctx* ctx, const float* x1, const float* x2, int m, double f, double base,
+                                   double c1u, double c1v, float* X);
+/* projectPoints(X,P), reference src/viso.cpp:326-333 (e2h/h2e misc.h:90-124); X 3 x n, P 3x4, x 2 x n */
+int viso_project_points(viso_ctx* ctx, const double* X, int n, const double P[12], double* x);
+
+/* ---- get_inliers, reference src/viso.cpp:1509-1537.  X 3 x n, observe 4 x n ---- */
+int viso_get_inliers(viso_ctx* ctx, const double* X, const double* observe, int n, const double tr[6],
+                     const viso_param* param, int32_t* inliers, int32_t* n_inliers);
+/* ---- minimize_reproj, reference src/viso.cpp:1583-1623 (compute_J :1401-1497).  tr in/out, ok out ---- */
+int viso_minimize_reproj(viso_ctx* ctx, const double* X, const double* observe, int n, double tr[6],
+                         const viso_param* param, const int32_t* active, int n_active, int32_t* ok);
+/* ---- ransac_minimize_reproj, reference src/viso.cpp:1543-1580, with randomsample (:87-107) replaced by the
+ * host-supplied sample_table[param->ransac_iter][3].  tr in/out.  Optional diagnostics may be NULL:
+ * hyp_tr[H][6], hyp_ok[H], hyp_count[H], best_hyp. */
+int viso_ransac_minimize_reproj(viso_ctx* ctx, const double* X, const double* observe, int n,
+                                const viso_param* param, const int32_t* sample_table,
+                                double tr[6], int32_t* inliers, int32_t* n_inliers, int32_t* ok,
+                                double* hyp_tr, int32_t* hyp_ok, int32_t* hyp_count, int32_t* best_hyp);
+/* default sample table: Knuth Algorithm S as in randomsample (viso.cpp:87-107), one std::mt19937(seed) stream */
+void viso_randomsample_table(uint32_t seed, int H, int N, int32_t* table);
+/* the pipeline's seeds -> ascending distinct triple mapping (see DESIGN.md "sample seeds"), N >= 3 */
+void viso_samples_from_seeds(const uint32_t* seeds, int H, int N, int32_t* table);
+
+/* ---- host bookkeeping kept outside the device: tr2mat (viso.cpp:109-133), F_from_P<double> (mvg.h:41-66 plus
+ * the normalisation at viso.cpp:1176-1180), pose = pose * inv(tr2mat(tr)) (viso.cpp:1315-1321) ---- */
+void viso_tr2mat(const double tr[6], double T[16]);
+void viso_F_from_P(const double P1[12], const double P2[12], int normalise, double F[9]);
+int viso_pose_update(const double pose[16], const double tr[6], double pose_out[16]);
+
+/* ==== batched sequence pipeline: the per-frame loop of sequence_odometry, reference src/viso.cpp:1205-1327,
+ * for all frames of a sequence at once (frame pairs are independent given features: the pose never feeds back,
+ * viso.cpp:1208-1222 vs :1317-1321).  Stereo match + sort + triangulate per frame; two temporal matches, circle
+ * closure, gather, RANSAC + Gauss-Newton per frame pair.  ==== */
+int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int max_ransac_iter, viso_seq** seq);
+void viso_seq_destroy(viso_seq* seq);
+/* F, base, f, cu, cv from P1,P2 exactly as viso.cpp:1176-1187 */
+int viso_seq_set_calib(viso_seq* seq, const double P1[12], const double P2[12]);
+/* host -> device copy of one frame's features (through pinned staging, asynchronous on the context stream) */
+int viso_seq_upload_frame(viso_seq* seq, int t, const float* kpL, int nL, const float* kpR, int nR,
+                          const float* dL, const float* dR);
+/* enqueue the whole pipeline for frames [0, n_frames).  seeds: host [n_frames][ransac_iter][3] uint32 (copied). */
+int viso_seq_run(viso_seq* seq, const viso_param* param, const uint32_t* seeds);
+/* same but the seeds are already on the device from a previous viso_seq_run / viso_seq_set_seeds */
+int viso_seq_set_seeds(viso_seq* seq, const uint32_t* seeds, int ransac_iter);
+int viso_seq_run_resident(viso_seq* seq, const viso_param* param);
+/* device -> host: records[n_frames] (record 0 zero: the first frame has no pose); synchronises */
+int viso_seq_download(viso_seq* seq, viso_record* records);
+/* rank-0 bookkeeping of viso.cpp:1189-1190,1313-1321: poses[0] = I, one 4x4 appended per ok record. returns count */
+int viso_chain_poses(const viso_record* records, int n_frames, double* poses /* (n_frames) x 16 */);
+/* algorithmic HBM bytes of the sad_match launch of one viso_seq_run (SURVEY 8d formula, int16 layout) and the
+ * number of SAD candidate pairs it evaluated (valid after viso_seq_download) */
+int viso_seq_stats(viso_seq* seq, int64_t* match_bytes, int64_t* sad_pairs);
+/* elapsed ms of the sad_match kernel in the last run (CUDA events on the context stream) */
+int viso_seq_match_ms(viso_seq* seq, float* ms);
+/* parity-test getters (host copies).  which: 0 = stereo (frame t), 1 = temporal left (t vs t-1), 2 = temporal right */
+int viso_seq_get_dense(viso_seq* seq, int which, int t, int32_t* out4 /* n x 4: idx,d1,d2,valid */, int32_t* n);
+int viso_seq_get_lr_matches(viso_seq* seq, int t, int32_t* matches3, int32_t* n);
+int viso_seq_get_circ(viso_seq* seq, int t, int32_t* circ4, int32_t* pcl2, int32_t* n);
+int viso_seq_get_inliers(viso_seq* seq, int t, int32_t* inliers, int32_t* n);
+int viso_seq_get_hyp(viso_seq* seq, int t, double* hyp_tr, int32_t* hyp_ok, int32_t* hyp_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

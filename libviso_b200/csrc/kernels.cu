@@ -1,0 +1,1212 @@
+/*
+ * kernels.cu -- hand-written sm_100a kernels for the libviso hot path.
+ *
+ * Compile with -fmad=false: the FP64 estimation code must evaluate exactly the reference's expressions
+ * (separate multiply and add, as a stock x86-64 build of the reference does) so that Jacobians, normal
+ * equations, LU pivots and inlier decisions agree bit for bit with the CPU path.  Device sin/cos are the only
+ * operations that can differ from glibc in the last place.
+ *
+ * Kernel inventory (DESIGN.md has the roofline for each):
+ *   pack_desc_kernel      f32 cv::Mat descriptors -> biased u16 rows (+ row sum), domain check       [HBM]
+ *   grid_build_kernel     counting sort of a keypoint set into 16-px cells                            [latency]
+ *   sad_match_kernel      match_desc (viso.cpp:668-722): radius search + top-K + Sampson + SAD argmin  [L1/ALU/HBM]
+ *   compact_sort_kernel   Match compaction, libstdc++ introsort order (viso.cpp:724), collect_matches
+ *                         (viso.cpp:501-514) + triangulate_rectified<double> (viso.cpp:1137-1154)      [latency]
+ *   circle_kernel         match_circle (viso.cpp:206-243) + circular gather (viso.cpp:1291-1305)       [latency]
+ *   ransac_hyp_kernel     3-point Gauss-Newton per hypothesis (viso.cpp:1555-1562, 1583-1623)          [FP64]
+ *   ransac_score_kernel   get_inliers count per hypothesis (viso.cpp:1509-1537)                        [FP64]
+ *   ransac_final_kernel   first-best selection, refine on the support set, final support (viso.cpp:1564-1576)
+ *   gn_kernel / inliers_kernel / triangulate / project / circle tables: standalone entry points
+ */
+#include "viso_dev.h"
+#include "introsort.h"
+
+#include <math_constants.h>
+
+#define FULL 0xffffffffu
+
+/* ------------------------------------------------------------------------------------------------ helpers */
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ unsigned warp_sum_u(unsigned v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+/* ordered compaction step for a CTA of (blockDim.x) threads: returns this thread's output slot (valid only when
+ * flag) and advances *base_io (a per-thread copy of the running total, identical in all threads). */
+__device__ __forceinline__ int block_compact_slot(bool flag, int& base_io, int* warp_tot /* smem[32] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned b = __ballot_sync(FULL, flag);
+    int pre = __popc(b & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[warp] = __popc(b);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+        int c = warp_tot[w];
+        if (w < warp) off += c;
+        tot += c;
+    }
+    __syncthreads();
+    int slot = base_io + off + pre;
+    base_io += tot;
+    return slot;
+}
+
+/* ------------------------------------------------------------------------------------------------ pack */
+
+__global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restrict__ jobs, int dlen, int* err)
+{
+    const PackJob job = jobs[blockIdx.y];
+    const int n = *job.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * 8 + warp; row < n; row += gridDim.x * 8) {
+        const float* src = job.d + (size_t)row * dlen;
+        unsigned u[4];
+        unsigned sum = 0;
+        int bad = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int k = lane * 4 + e;
+            unsigned v = 0;
+            if (k < dlen) {
+                float f = src[k];
+                float r = truncf(f);
+                if (!(f == r) || !(fabsf(f) <= 1023.f)) bad = 1;
+                else v = (unsigned)((int)r + 1024);
+            }
+            u[e] = v;
+            sum += v;
+        }
+        sum = warp_sum_u(sum);
+        uint2 w;
+        w.x = u[0] | (u[1] << 16);
+        w.y = u[2] | (u[3] << 16);
+        if (lane == 31) w.y = sum; /* elements 126,127 carry the row sum */
+        reinterpret_cast<uint2*>(job.out + (size_t)row * VISO_DESC_U16)[lane] = w;
+        if (bad) atomicOr(err, 1);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ grid */
+
+__device__ __forceinline__ int cell_coord(float v, int g)
+{
+    int c = __float2int_rd(v * (1.0f / VISO_GRID_CS));
+    return min(max(c, 0), g - 1);
+}
+
+__global__ void __launch_bounds__(512) grid_build_kernel(const GridJob* __restrict__ jobs, GridCfg g)
+{
+    extern __shared__ int sm[];
+    const int ncell = g.gx * g.gy;
+    int* hist = sm;               /* ncell + 1 */
+    int* cursor = sm + ncell + 1; /* ncell */
+    const GridJob job = jobs[blockIdx.x];
+    const int n = *job.n;
+    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) hist[c] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float2 p = job.xy[i];
+        atomicAdd(&hist[cell_coord(p.y, g.gy) * g.gx + cell_coord(p.x, g.gx)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) { /* exclusive scan: each lane owns a contiguous chunk */
+        const int lane = threadIdx.x;
+        const int chunk = (ncell + 31) / 32;
+        const int b = lane * chunk, e = min(b + chunk, ncell);
+        int s = 0;
+        for (int c = b; c < e; ++c) s += hist[c];
+        int incl = warp_incl_scan(s, lane);
+        int run = incl - s;
+        for (int c = b; c < e; ++c) { int h = hist[c]; hist[c] = run; run += h; }
+        if (lane == 31) hist[ncell] = incl;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) {
+        int v = hist[c];
+        job.cell_start[c] = v;
+        if (c < ncell) cursor[c] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float2 p = job.xy[i];
+        int pos = atomicAdd(&cursor[cell_coord(p.y, g.gy) * g.gx + cell_coord(p.x, g.gx)], 1);
+        job.sxy[pos] = p;
+        job.sidx[pos] = i;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ match */
+
+/* sampsonDistance + algebricDistance, viso.cpp:652-666, 390-407: literal operation order (no FMA) */
+__device__ __forceinline__ double sampson_dev(const double* F, float p1x, float p1y, float p2x, float p2y)
+{
+    double Fx0 = F[0] * p1x + F[1] * p1y + F[2];
+    double Fx1 = F[3] * p1x + F[4] * p1y + F[5];
+    double Ftx0 = F[0] * p2x + F[3] * p2y + F[6];
+    double Ftx1 = F[1] * p2x + F[4] * p2y + F[7];
+    float a0 = p1x, a1 = p1y, a2 = 1.f, b0 = p2x, b1 = p2y, b2 = 1.f;
+    double alg = b0 * F[0] * a0 + b0 * F[1] * a1 + b0 * F[2] * a2 +
+                 b1 * F[3] * a0 + b1 * F[4] * a1 + b1 * F[5] * a2 +
+                 b2 * F[6] * a0 + b2 * F[7] * a1 + b2 * F[8] * a2;
+    float ad = (float)alg;
+    float ad2 = __fmul_rn(ad, ad);
+    return (double)ad2 / (Fx0 * Fx0 + Fx1 * Fx1 + Ftx0 * Ftx0 + Ftx1 * Ftx1);
+}
+
+__device__ __forceinline__ float l1_dist(float qx, float qy, float tx, float ty)
+{
+    return __fadd_rn(fabsf(__fsub_rn(tx, qx)), fabsf(__fsub_rn(ty, qy)));
+}
+
+__device__ __forceinline__ bool key_greater(float d1, int i1, float d2, int i2)
+{
+    return d1 > d2 || (d1 == d2 && i1 > i2);
+}
+
+struct WarpScratch {
+    int rowS0[32];
+    int rowPre[33];
+    unsigned hist[VISO_HIST_BINS];
+    float tieD[VISO_TIE_CAP];
+    int tieI[VISO_TIE_CAP];
+};
+
+/* Enumerate, warp-cooperatively and flattened over grid rows, every target point in the cells overlapping the
+ * L1 diamond of radius r around (qx,qy).  f(in, dist, idx) is called by all 32 lanes for each chunk of 32. */
+template <class Fn>
+__device__ __forceinline__ void enumerate_candidates(const SetView& t, GridCfg g, float qx, float qy, float r,
+                                                     WarpScratch& ws, int lane, Fn&& f)
+{
+    const float slack = 1.0f + 4e-6f * (fabsf(qx) + fabsf(qy) + r);
+    const int cy0 = cell_coord(qy - r - slack, g.gy), cy1 = cell_coord(qy + r + slack, g.gy);
+    for (int rg = cy0; rg <= cy1; rg += 32) {
+        const int cy = rg + lane;
+        int s0 = 0, len = 0;
+        if (cy <= cy1) {
+            const float lo = (cy == 0) ? -CUDART_INF_F : (float)(cy * VISO_GRID_CS);
+            const float hi = (cy == g.gy - 1) ? CUDART_INF_F : (float)((cy + 1) * VISO_GRID_CS);
+            const float dymin = fmaxf(0.f, fmaxf(lo - qy, qy - hi));
+            const float rem = r - dymin + slack;
+            if (rem >= 0.f) {
+                const int cx0 = cell_coord(qx - rem, g.gx), cx1 = cell_coord(qx + rem, g.gx);
+                s0 = t.cell_start[cy * g.gx + cx0];
+                len = t.cell_start[cy * g.gx + cx1 + 1] - s0;
+            }
+        }
+        const int incl = warp_incl_scan(len, lane);
+        __syncwarp();
+        ws.rowS0[lane] = s0;
+        ws.rowPre[lane] = incl - len;
+        if (lane == 31) ws.rowPre[32] = incl;
+        __syncwarp();
+        const int total = __shfl_sync(FULL, incl, 31);
+        int row = 0;
+        for (int base = 0; base < total; base += 32) {
+            const int fl = base + lane;
+            const bool in = fl < total;
+            float dist = CUDART_INF_F;
+            int idx = -1;
+            if (in) {
+                while (fl >= ws.rowPre[row + 1]) ++row;
+                const int p = ws.rowS0[row] + (fl - ws.rowPre[row]);
+                const float2 xy = t.sxy[p];
+                idx = t.sidx[p];
+                dist = l1_dist(qx, qy, xy.x, xy.y);
+            }
+            f(in, dist, idx);
+        }
+    }
+}
+
+/* upper bound on the number of points enumerate_candidates visits (sum of the span lengths): if it is <= K the
+ * top-K truncation cannot bind and one enumeration pass suffices */
+__device__ __forceinline__ int enumerate_bound(const SetView& t, GridCfg g, float qx, float qy, float r, int lane)
+{
+    const float slack = 1.0f + 4e-6f * (fabsf(qx) + fabsf(qy) + r);
+    const int cy0 = cell_coord(qy - r - slack, g.gy), cy1 = cell_coord(qy + r + slack, g.gy);
+    int tot = 0;
+    for (int cy = cy0 + lane; cy <= cy1; cy += 32) {
+        const float lo = (cy == 0) ? -CUDART_INF_F : (float)(cy * VISO_GRID_CS);
+        const float hi = (cy == g.gy - 1) ? CUDART_INF_F : (float)((cy + 1) * VISO_GRID_CS);
+        const float dymin = fmaxf(0.f, fmaxf(lo - qy, qy - hi));
+        const float rem = r - dymin + slack;
+        if (rem >= 0.f) {
+            const int cx0 = cell_coord(qx - rem, g.gx), cx1 = cell_coord(qx + rem, g.gx);
+            tot += t.cell_start[cy * g.gx + cx1 + 1] - t.cell_start[cy * g.gx + cx0];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+    return tot;
+}
+
+__device__ __forceinline__ int dist_bin(float dist, float scale)
+{
+    return min(VISO_HIST_BINS - 1, (int)(dist * scale));
+}
+
+/*
+ * match_desc, viso.cpp:668-722.  One warp per query.
+ *
+ * Reference semantics restated set-wise: with D0 = L1(query, target 0) if that is <= radius
+ * (else +inf), the scanned candidates are the K smallest keys (L1, index) among
+ *     L = { j : L1_j <= radius and L1_j < D0 }
+ * (target 0 terminates the reference's scan, viso.cpp:693, and sorts first inside its distance group, so exactly
+ * the strictly closer points are scanned).  Over that set: best = min SAD, ties to the LARGEST key (the last one
+ * in scan order, viso.cpp:703), best_d2 = second smallest SAD with multiplicity.  Sampson-gated candidates
+ * (viso.cpp:695-701) still occupy a top-K slot but are not compared.
+ *
+ * SAD on biased u16 rows: sum|a-b| = sum(a) + sum(b) - 2*sum(min(a,b)); VIMNMX.U16x2 + IADD, 16 lanes x uint4
+ * per 256-byte row, two candidates per warp step.
+ */
+__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32)
+sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, unsigned long long* sad_pairs)
+{
+    __shared__ WarpScratch wscr[VISO_MATCH_WARPS];
+    const MatchJob job = jobs[blockIdx.y];
+    const MatchParamsDev& P = mp.p[job.mode];
+    const int nq = *job.q.n, nt = *job.t.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane & 15;
+    WarpScratch& ws = wscr[warp];
+    const float r = P.radius;
+    const int K = P.K;
+    const float bscale = (float)VISO_HIST_BINS / (r + 1.0f);
+    unsigned long long pairs = 0;
+
+    const int q_end = min(nq, (int)(blockIdx.x + 1) * VISO_MATCH_QPC);
+    for (int qi = blockIdx.x * VISO_MATCH_QPC + warp; qi < q_end; qi += VISO_MATCH_WARPS) {
+        const int q = job.q.sidx[qi]; /* spatially sorted processing order */
+        const float2 qxy = job.q.xy[q];
+        const float qx = qxy.x, qy = qxy.y;
+        uint4 qd = __ldg(reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + h);
+        const unsigned qsum = __shfl_sync(FULL, qd.w, 15);
+
+        int b1 = INT_MAX, b2 = INT_MAX, bidx = -1;
+        float bdist = -1.f;
+
+        if (nt > 0) {
+            /* index 0 terminator */
+            const float2 t0 = job.t.xy[0];
+            const float d0 = l1_dist(qx, qy, t0.x, t0.y);
+            const float D0 = (d0 <= r) ? d0 : CUDART_INF_F;
+
+            /* top-K threshold: (Tbin, Td, Ti); candidates with bin < Tbin, or bin == Tbin and key <= (Td,Ti) */
+            int Tbin = INT_MAX;
+            float Td = CUDART_INF_F;
+            int Ti = INT_MAX;
+            const int bound = enumerate_bound(job.t, g, qx, qy, r, lane);
+            if (bound > K) {
+                for (int b = lane; b < VISO_HIST_BINS; b += 32) ws.hist[b] = 0;
+                __syncwarp();
+                int cnt = 0;
+                enumerate_candidates(job.t, g, qx, qy, r, ws, lane, [&](bool in, float dist, int idx) {
+                    const bool inL = in && dist <= r && dist < D0;
+                    if (inL) atomicAdd(&ws.hist[dist_bin(dist, bscale)], 1u);
+                    cnt += __popc(__ballot_sync(FULL, inL));
+                });
+                __syncwarp();
+                if (cnt > K) {
+                    /* find the bin where the cumulative count reaches K */
+                    unsigned c[4];
+                    unsigned s = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { c[e] = ws.hist[lane * 4 + e]; s += c[e]; }
+                    const int incl = warp_incl_scan((int)s, lane);
+                    const unsigned hit = __ballot_sync(FULL, incl >= K);
+                    const int hl = __ffs(hit) - 1;
+                    int tb = 0, before = 0;
+                    if (lane == hl) {
+                        int run = incl - (int)s;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (run + (int)c[e] >= K) { tb = lane * 4 + e; before = run; break; }
+                            run += (int)c[e];
+                        }
+                    }
+                    tb = __shfl_sync(FULL, tb, hl);
+                    before = __shfl_sync(FULL, before, hl);
+                    const int nb = (int)ws.hist[tb];
+                    const int m = K - before; /* 1..nb keys of bin tb are kept */
+                    Tbin = tb;
+                    if (m < nb) {
+                        if (nb <= VISO_TIE_CAP) {
+                            int fill = 0;
+                            enumerate_candidates(job.t, g, qx, qy, r, ws, lane, [&](bool in, float dist, int idx) {
+                                const bool hitb = in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb;
+                                const unsigned bm = __ballot_sync(FULL, hitb);
+                                if (hitb) {
+                                    const int o = fill + __popc(bm & ((1u << lane) - 1));
+                                    ws.tieD[o] = dist;
+                                    ws.tieI[o] = idx;
+                                }
+                                fill += __popc(bm);
+                            });
+                            __syncwarp();
+                            /* the key of rank m-1 inside the bin */
+                            float selD = 0.f; int selI = 0; bool have = false;
+                            for (int e = lane; e < nb; e += 32) {
+                                const float de = ws.tieD[e]; const int ie = ws.tieI[e];
+                                int rank = 0;
+                                for (int o = 0; o < nb; ++o) rank += key_greater(de, ie, ws.tieD[o], ws.tieI[o]) ? 1 : 0;
+                                if (rank == m - 1) { selD = de; selI = ie; have = true; }
+                            }
+                            const unsigned hm = __ballot_sync(FULL, have);
+                            const int sl = __ffs(hm) - 1;
+                            Td = __shfl_sync(FULL, selD, sl);
+                            Ti = __shfl_sync(FULL, selI, sl);
+                        } else {
+                            /* pathological tie bin: m successive minimum searches (exact, slow) */
+                            float curD = -1.f; int curI = -1;
+                            for (int it = 0; it < m; ++it) {
+                                float bestD = CUDART_INF_F; int bestI = INT_MAX;
+                                enumerate_candidates(job.t, g, qx, qy, r, ws, lane, [&](bool in, float dist, int idx) {
+                                    if (in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb &&
+                                        key_greater(dist, idx, curD, curI) && key_greater(bestD, bestI, dist, idx)) {
+                                        bestD = dist; bestI = idx;
+                                    }
+                                });
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    const float od = __shfl_xor_sync(FULL, bestD, o);
+                                    const int oi = __shfl_xor_sync(FULL, bestI, o);
+                                    if (key_greater(bestD, bestI, od, oi)) { bestD = od; bestI = oi; }
+                                }
+                                curD = bestD; curI = bestI;
+                            }
+                            Td = curD; Ti = curI;
+                        }
+                    }
+                }
+            }
+
+            /* final pass: Sampson gate + SAD, two candidates per step (one per half warp) */
+            enumerate_candidates(job.t, g, qx, qy, r, ws, lane, [&](bool in, float dist, int idx) {
+                bool take = in && dist <= r && dist < D0;
+                if (take && Tbin != INT_MAX) {
+                    const int bin = dist_bin(dist, bscale);
+                    take = bin < Tbin || (bin == Tbin && !key_greater(dist, idx, Td, Ti));
+                }
+                if (take && P.epipolar) {
+                    const float2 txy = job.t.xy[idx];
+                    const double sd = sampson_dev(P.F, qx, qy, txy.x, txy.y);
+                    if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
+                }
+                unsigned m = __ballot_sync(FULL, take);
+                pairs += __popc(m);
+                while (m) {
+                    const int la = __ffs(m) - 1;
+                    m &= m - 1;
+                    int lb = -1;
+                    if (m) { lb = __ffs(m) - 1; m &= m - 1; }
+                    const int src = (lane < 16) ? la : lb;
+                    const bool cv = src >= 0;
+                    const int cidx = __shfl_sync(FULL, idx, cv ? src : 0);
+                    const float cdist = __shfl_sync(FULL, dist, cv ? src : 0);
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (cv) v = __ldg(reinterpret_cast<const uint4*>(job.t.desc + (size_t)cidx * VISO_DESC_U16) + h);
+                    unsigned acc = __vminu2(qd.x, v.x) + __vminu2(qd.y, v.y) + __vminu2(qd.z, v.z);
+                    if (h != 15) acc += __vminu2(qd.w, v.w);
+                    unsigned s = (acc & 0xffffu) + (acc >> 16);
+                    s += __shfl_xor_sync(FULL, s, 8);
+                    s += __shfl_xor_sync(FULL, s, 4);
+                    s += __shfl_xor_sync(FULL, s, 2);
+                    s += __shfl_xor_sync(FULL, s, 1);
+                    const unsigned tsum = __shfl_sync(FULL, v.w, (lane & 16) | 15);
+                    const int sad = (int)(qsum + tsum - 2u * s);
+                    if (cv) {
+                        if (sad < b1) { b2 = b1; b1 = sad; bdist = cdist; bidx = cidx; }
+                        else if (sad == b1) { b2 = b1; if (key_greater(cdist, cidx, bdist, bidx)) { bdist = cdist; bidx = cidx; } }
+                        else if (sad < b2) b2 = sad;
+                    }
+                }
+            });
+        }
+        /* merge the two half-warp states */
+        {
+            const int ob1 = __shfl_sync(FULL, b1, 16), ob2 = __shfl_sync(FULL, b2, 16), oidx = __shfl_sync(FULL, bidx, 16);
+            const float odist = __shfl_sync(FULL, bdist, 16);
+            const int hi1 = max(b1, ob1), lo2 = min(b2, ob2);
+            if (ob1 < b1 || (ob1 == b1 && oidx >= 0 && key_greater(odist, oidx, bdist, bidx))) { bidx = oidx; bdist = odist; }
+            b1 = min(b1, ob1);
+            b2 = min(hi1, lo2);
+        }
+        if (lane == 0) {
+            int valid = 0;
+            if (bidx >= 0) {
+                if (P.second_best) {
+                    const double d2 = (b2 == INT_MAX) ? 1.7976931348623157e308 : (double)b2;
+                    valid = ((double)b1 < d2 * P.ratio) ? 1 : 0; /* viso.cpp:715 */
+                } else
+                    valid = 1;
+            }
+            job.out[q] = make_int4(bidx, b1, b2, valid);
+        }
+    }
+    if (sad_pairs) {
+        pairs = __shfl_sync(FULL, pairs, 0);
+        if (lane == 0 && pairs) atomicAdd(sad_pairs, pairs);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ sort */
+
+/*
+ * Per frame: (1) compaction of the valid dense results in query order into Match(i, best_idx, best_d1)
+ * (viso.cpp:711-722), (2) the reference's std::sort order (viso.cpp:724) via the restated libstdc++ introsort
+ * run by one thread, (3) pos_of_query inverse table, collect_matches (viso.cpp:501-514) and
+ * triangulate_rectified<double> (viso.cpp:1146-1152).
+ */
+__global__ void __launch_bounds__(256) compact_sort_kernel(const SortJob* __restrict__ jobs, ParamDev P)
+{
+    __shared__ int warp_tot[32];
+    const SortJob job = jobs[blockIdx.x];
+    const int n = *job.n;
+    int base = 0;
+    for (int start = 0; start < n; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        int4 r = make_int4(0, 0, 0, 0);
+        if (i < n) {
+            r = job.dense[i];
+            if (job.pos_of_query) job.pos_of_query[i] = -1;
+        }
+        const bool flag = i < n && r.w != 0;
+        const int slot = block_compact_slot(flag, base, warp_tot);
+        if (flag) {
+            job.matches[3 * slot + 0] = i;
+            job.matches[3 * slot + 1] = r.x;
+            job.matches[3 * slot + 2] = r.y;
+        }
+    }
+    const int M = base;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        viso_sort::sort(reinterpret_cast<viso_sort::M3*>(job.matches), M);
+        *job.count = M;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < M; p += blockDim.x) {
+        const int i1 = job.matches[3 * p], i2 = job.matches[3 * p + 1];
+        if (job.pos_of_query) job.pos_of_query[i1] = p;
+        if (job.x) {
+            const float2 a = job.kp1[i1], b = job.kp2[i2];
+            const double u1 = a.x, v1 = a.y, u2 = b.x, v2 = b.y;
+            const int S = job.stride;
+            job.x[0 * S + p] = u1; job.x[1 * S + p] = v1; job.x[2 * S + p] = u2; job.x[3 * S + p] = v2;
+            if (job.X) {
+                const double d = u1 - u2;
+                job.X[0 * S + p] = P.base * (u1 - P.cu) / d;
+                job.X[1 * S + p] = P.base * (v1 - P.cv) / d;
+                job.X[2 * S + p] = P.f * P.base / d;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ circle */
+
+/*
+ * match_circle, viso.cpp:206-243, for match lists produced by match_desc (unique query index per list): the four
+ * nested scans collapse to table lookups -- match11 and match22 are read from the dense per-query results, the
+ * position k in match_lr_prev from pos_of_query of the previous frame.  Output order = ascending position i in
+ * match_lr, as in the reference.  Also gathers x_c / Xp_c (viso.cpp:1291-1305).
+ */
+__global__ void __launch_bounds__(256) circle_kernel(const CircleJob* __restrict__ jobs)
+{
+    __shared__ int warp_tot[32];
+    const CircleJob job = jobs[blockIdx.x];
+    const int M = *job.lr_count, Mp = *job.lrp_count, npl = *job.n_prev_left;
+    const int S = job.stride;
+    int base = 0;
+    for (int start = 0; start < M; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        bool flag = false;
+        int il = 0, ir = 0, ilp = 0, irp = 0, k = 0;
+        if (i < M) {
+            il = job.lr[3 * i]; ir = job.lr[3 * i + 1];
+            const int4 a = job.m11[il];
+            if (a.w) {
+                ilp = a.x;
+                if (ilp >= 0 && ilp < npl) {
+                    k = job.pos_prev[ilp];
+                    if (k >= 0 && k < Mp) {
+                        irp = job.lrp[3 * k + 1];
+                        const int4 b = job.m22[ir];
+                        flag = b.w && b.x == irp;
+                    }
+                }
+            }
+        }
+        const int c = block_compact_slot(flag, base, warp_tot);
+        if (flag) {
+            job.circ4[4 * c] = il; job.circ4[4 * c + 1] = ir; job.circ4[4 * c + 2] = ilp; job.circ4[4 * c + 3] = irp;
+            job.pcl2[2 * c] = i; job.pcl2[2 * c + 1] = k;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) job.x_c[r * S + c] = job.x[r * S + i];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) job.Xp_c[r * S + c] = job.Xp[r * S + k];
+        }
+    }
+    if (threadIdx.x == 0) {
+        *job.n_circ = base;
+        viso_record_dev rec;
+        for (int j = 0; j < 6; ++j) rec.tr[j] = 0;
+        rec.ok = 0; rec.n_inliers = 0; rec.n_circ = base; rec.best_hyp = -1;
+        *job.rec = rec;
+    }
+}
+
+/* generic (standalone) variant working from explicit lookup tables, for viso_match_circle() */
+__global__ void circle_tables_kernel(const int* __restrict__ m, int n, int* table, int table_n, int key_col, int val_mode,
+                                     int* err)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int key = m[3 * i + key_col];
+    if (key < 0 || key >= table_n) return;
+    const int val = val_mode ? i : m[3 * i + 1];
+    const int old = atomicCAS(&table[key], -1, val);
+    if (old != -1) atomicOr(err, 2);
+}
+
+__global__ void __launch_bounds__(256)
+circle_generic_kernel(const int* __restrict__ lr, int nlr, const int* __restrict__ lrp, int nlrp,
+                      const int* __restrict__ t11, int n_t11, const int* __restrict__ tlrp, int n_tlrp,
+                      const int* __restrict__ t22, int n_t22, int* circ4, int* pcl3, int* n_out)
+{
+    __shared__ int warp_tot[32];
+    int base = 0;
+    for (int start = 0; start < nlr; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        bool flag = false;
+        int il = 0, ir = 0, ilp = 0, irp = 0, k = 0;
+        if (i < nlr) {
+            il = lr[3 * i]; ir = lr[3 * i + 1];
+            if (il >= 0 && il < n_t11 && (ilp = t11[il]) >= 0 && ilp < n_tlrp && (k = tlrp[ilp]) >= 0 && k < nlrp) {
+                irp = lrp[3 * k + 1];
+                flag = ir >= 0 && ir < n_t22 && t22[ir] == irp && irp >= 0;
+            }
+        }
+        const int c = block_compact_slot(flag, base, warp_tot);
+        if (flag) {
+            circ4[4 * c] = il; circ4[4 * c + 1] = ir; circ4[4 * c + 2] = ilp; circ4[4 * c + 3] = irp;
+            pcl3[3 * c] = i; pcl3[3 * c + 1] = k; pcl3[3 * c + 2] = 0;
+        }
+    }
+    if (threadIdx.x == 0) *n_out = base;
+}
+
+/* ------------------------------------------------------------------------------------------------ estimation */
+
+struct Rot {
+    double r00, r01, r02, r10, r11, r12, r20, r21, r22;
+    double rdrx10, rdrx11, rdrx12, rdrx20, rdrx21, rdrx22;
+    double rdry00, rdry01, rdry02, rdry10, rdry11, rdry12, rdry20, rdry21, rdry22;
+    double rdrz00, rdrz01, rdrz10, rdrz11, rdrz20, rdrz21;
+    double tx, ty, tz;
+};
+
+/* viso.cpp:1406-1424 */
+__device__ __forceinline__ void make_rot(const double* tr, Rot& R, bool derivs)
+{
+    const double rx = tr[0], ry = tr[1], rz = tr[2];
+    R.tx = tr[3]; R.ty = tr[4]; R.tz = tr[5];
+    const double sx = sin(rx), cx = cos(rx), sy = sin(ry);
+    const double cy = cos(ry), sz = sin(rz), cz = cos(rz);
+    R.r00 = +cy * cz;                R.r01 = -cy * sz;                R.r02 = +sy;
+    R.r10 = +sx * sy * cz + cx * sz; R.r11 = -sx * sy * sz + cx * cz; R.r12 = -sx * cy;
+    R.r20 = -cx * sy * cz + sx * sz; R.r21 = +cx * sy * sz + sx * cz; R.r22 = +cx * cy;
+    if (derivs) {
+        R.rdrx10 = +cx * sy * cz - sx * sz; R.rdrx11 = -cx * sy * sz - sx * cz; R.rdrx12 = -cx * cy;
+        R.rdrx20 = +sx * sy * cz + cx * sz; R.rdrx21 = -sx * sy * sz + cx * cz; R.rdrx22 = -sx * cy;
+        R.rdry00 = -sy * cz;      R.rdry01 = +sy * sz;      R.rdry02 = +cy;
+        R.rdry10 = +sx * cy * cz; R.rdry11 = -sx * cy * sz; R.rdry12 = +sx * sy;
+        R.rdry20 = -cx * cy * cz; R.rdry21 = +cx * cy * sz; R.rdry22 = -cx * sy;
+        R.rdrz00 = -cy * sz;                R.rdrz01 = -cy * cz;
+        R.rdrz10 = -sx * sy * sz + cx * cz; R.rdrz11 = -sx * sy * cz - cx * sz;
+        R.rdrz20 = +cx * sy * sz + sx * cz; R.rdrz21 = +cx * sy * cz - sx * sz;
+    }
+}
+
+/* prediction of one point, viso.cpp:1441-1443, 1452, 1486-1489 */
+__device__ __forceinline__ void predict_point(const Rot& R, const ParamDev& P, double X1p, double Y1p, double Z1p,
+                                              double pred[4])
+{
+    const double X1c = R.r00 * X1p + R.r01 * Y1p + R.r02 * Z1p + R.tx;
+    const double Y1c = R.r10 * X1p + R.r11 * Y1p + R.r12 * Z1p + R.ty;
+    const double Z1c = R.r20 * X1p + R.r21 * Y1p + R.r22 * Z1p + R.tz;
+    const double X2c = X1c - P.base;
+    pred[0] = P.f * X1c / Z1c + P.cu;
+    pred[1] = P.f * Y1c / Z1c + P.cv;
+    pred[2] = P.f * X2c / Z1c + P.cu;
+    pred[3] = P.f * Y1c / Z1c + P.cv;
+}
+
+/* inlier test, viso.cpp:1527-1533 */
+__device__ __forceinline__ bool inlier_point(const Rot& R, const ParamDev& P, const double* X, const double* obs,
+                                             int stride, int i)
+{
+    double pred[4];
+    predict_point(R, P, X[i], X[stride + i], X[2 * stride + i], pred);
+    const double e0 = obs[i] - pred[0], e1 = obs[stride + i] - pred[1];
+    const double e2 = obs[2 * stride + i] - pred[2], e3 = obs[3 * stride + i] - pred[3];
+    const double err2 = e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+    return err2 < P.thr2;
+}
+
+/* Jacobian rows + weighted residuals of one point, viso.cpp:1441-1495 (literal; no shortcuts for the constant
+ * derivative columns so that non-finite inputs propagate exactly as in the reference).
+ * out: 4 rows x 7 (6 Jacobian columns + residual). */
+__device__ __forceinline__ void point_rows(const Rot& R, const ParamDev& P, double X1p, double Y1p, double Z1p,
+                                           double weight, const double ob[4], double out[4][7])
+{
+    const double X1c = R.r00 * X1p + R.r01 * Y1p + R.r02 * Z1p + R.tx;
+    const double Y1c = R.r10 * X1p + R.r11 * Y1p + R.r12 * Z1p + R.ty;
+    const double Z1c = R.r20 * X1p + R.r21 * Y1p + R.r22 * Z1p + R.tz;
+    const double X2c = X1c - P.base;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double X1cd, Y1cd, Z1cd;
+        switch (j) {
+        case 0: X1cd = 0;
+            Y1cd = R.rdrx10 * X1p + R.rdrx11 * Y1p + R.rdrx12 * Z1p;
+            Z1cd = R.rdrx20 * X1p + R.rdrx21 * Y1p + R.rdrx22 * Z1p;
+            break;
+        case 1: X1cd = R.rdry00 * X1p + R.rdry01 * Y1p + R.rdry02 * Z1p;
+            Y1cd = R.rdry10 * X1p + R.rdry11 * Y1p + R.rdry12 * Z1p;
+            Z1cd = R.rdry20 * X1p + R.rdry21 * Y1p + R.rdry22 * Z1p;
+            break;
+        case 2: X1cd = R.rdrz00 * X1p + R.rdrz01 * Y1p;
+            Y1cd = R.rdrz10 * X1p + R.rdrz11 * Y1p;
+            Z1cd = R.rdrz20 * X1p + R.rdrz21 * Y1p;
+            break;
+        case 3: X1cd = 1; Y1cd = 0; Z1cd = 0; break;
+        case 4: X1cd = 0; Y1cd = 1; Z1cd = 0; break;
+        default: X1cd = 0; Y1cd = 0; Z1cd = 1; break;
+        }
+        out[0][j] = weight * P.f * (X1cd * Z1c - X1c * Z1cd) / (Z1c * Z1c);
+        out[1][j] = weight * P.f * (Y1cd * Z1c - Y1c * Z1cd) / (Z1c * Z1c);
+        out[2][j] = weight * P.f * (X1cd * Z1c - X2c * Z1cd) / (Z1c * Z1c);
+        out[3][j] = weight * P.f * (Y1cd * Z1c - Y1c * Z1cd) / (Z1c * Z1c);
+    }
+    double pred[4];
+    pred[0] = P.f * X1c / Z1c + P.cu;
+    pred[1] = P.f * Y1c / Z1c + P.cv;
+    pred[2] = P.f * X2c / Z1c + P.cu;
+    pred[3] = P.f * Y1c / Z1c + P.cv;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[r][6] = weight * (ob[r] - pred[r]);
+}
+
+/* weight, viso.cpp:1449: read from observe column i (the LOOP index, not active[i]) */
+__device__ __forceinline__ double weight_of(const ParamDev& P, double obs0_col_i)
+{
+    return 1.0 / (fabs(obs0_col_i - P.cu) / fabs(P.cu) + 0.05);
+}
+
+/* cv::solve(JtJ, Jtr, p, DECOMP_LU) == OpenCV hal LUImpl<double>, m = 6, one right-hand side (viso.cpp:1602).
+ * A is the full symmetric 6x6.  Returns false when a pivot is < 100*DBL_EPSILON. */
+__device__ __forceinline__ bool lu_solve6(double A[6][6], double b[6])
+{
+    const double eps = 2.220446049250313e-16 * 100;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        int k = i;
+        double best = fabs(A[i][i]);
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) {
+            const double v = fabs(A[j][i]);
+            if (v > best) { best = v; k = j; }
+        }
+        if (best < eps) return false;
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) {
+            if (k == j) {
+#pragma unroll
+                for (int c = i; c < 6; ++c) { const double t = A[i][c]; A[i][c] = A[j][c]; A[j][c] = t; }
+                const double t = b[i]; b[i] = b[j]; b[j] = t;
+            }
+        }
+        const double d = -1 / A[i][i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) {
+            const double alpha = A[j][i] * d;
+#pragma unroll
+            for (int c = i + 1; c < 6; ++c) A[j][c] += alpha * A[i][c];
+            b[j] += alpha * b[i];
+        }
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double s = b[i];
+#pragma unroll
+        for (int c = i + 1; c < 6; ++c) s -= A[i][c] * b[c];
+        b[i] = s / A[i][i];
+    }
+    return true;
+}
+
+/* NaN pivots: fabs(NaN) > best is false and best < eps is false, exactly like the reference's
+ * std::abs comparisons -- the solve "succeeds" with NaN output (and viso.cpp:1610 then reports convergence). */
+
+__device__ __forceinline__ void sample_from_seeds(const uint32_t* seeds, int N, int s[3])
+{
+    const uint32_t r0 = seeds[0], r1 = seeds[1], r2 = seeds[2];
+    int a = (int)(((unsigned long long)r0 * (unsigned long long)N) >> 32);
+    int b = (int)(((unsigned long long)r1 * (unsigned long long)(N - 1)) >> 32);
+    int c = (int)(((unsigned long long)r2 * (unsigned long long)(N - 2)) >> 32);
+    if (b >= a) b++;
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    if (c >= lo) c++;
+    if (c >= hi) c++;
+    int s0 = lo, s1 = hi, s2 = c;
+    if (s2 < s0) { const int t = s2; s2 = s1; s1 = s0; s0 = t; }
+    else if (s2 < s1) { const int t = s2; s2 = s1; s1 = t; }
+    s[0] = s0; s[1] = s1; s[2] = s2;
+}
+
+/*
+ * One thread per hypothesis: tr = 0, 3-point sample, Gauss-Newton (minimize_reproj with 3 active points),
+ * viso.cpp:1555-1562 + 1583-1623.  Sums run in the reference's row order 0..11.
+ */
+__global__ void __launch_bounds__(64) ransac_hyp_kernel(const RansacProb* __restrict__ probs, ParamDev P)
+{
+    const RansacProb& pb = probs[blockIdx.y];
+    const int hId = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *pb.n;
+    if (hId >= pb.H || n < pb.min_n || n < 1) return;
+    int s[3];
+    if (pb.table) { s[0] = pb.table[3 * hId]; s[1] = pb.table[3 * hId + 1]; s[2] = pb.table[3 * hId + 2]; }
+    else sample_from_seeds(pb.seeds + 3 * hId, n, s);
+    const int S = pb.stride;
+    double Xs[3][3], Os[3][4], w[3];
+    bool bad_index = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int a = s[i];
+        if (a < 0 || a >= n) { bad_index = true; a = 0; }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Xs[i][r] = pb.X[r * S + a];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Os[i][r] = pb.obs[r * S + a];
+        w[i] = weight_of(P, pb.obs[min(i, n - 1)]); /* columns 0,1,2 */
+    }
+    double tr[6] = {0, 0, 0, 0, 0, 0};
+    int ok = 0;
+    if (!bad_index) {
+        for (int it = 0; it < 100; ++it) {
+            Rot R;
+            make_rot(tr, R, true);
+            double A[6][6], b[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                b[i] = 0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) A[i][j] = 0;
+            }
+#pragma unroll 1
+            for (int i = 0; i < 3; ++i) {
+                double rows[4][7];
+                point_rows(R, P, Xs[i][0], Xs[i][1], Xs[i][2], w[i], Os[i], rows);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                        for (int c = a; c < 6; ++c) A[a][c] += rows[r][a] * rows[r][c];
+                        b[a] += rows[r][a] * rows[r][6];
+                    }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = 0; c < a; ++c) A[a][c] = A[c][a];
+            if (!lu_solve6(A, b)) { ok = 0; break; }
+            bool conv = true;
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                if (b[j] > P.thresh) { conv = false; break; } /* fabs(p > thresh), viso.cpp:1610 */
+            if (conv) { ok = 1; break; }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) tr[j] = tr[j] + b[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) pb.hyp_tr[6 * hId + j] = tr[j];
+    pb.hyp_ok[hId] = ok;
+    pb.hyp_count[hId] = -1;
+}
+
+/* One warp per hypothesis: support-set size, viso.cpp:1563 (get_inliers, :1509-1537) */
+__global__ void __launch_bounds__(256) ransac_score_kernel(const RansacProb* __restrict__ probs, ParamDev P)
+{
+    const RansacProb& pb = probs[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int hId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n = *pb.n;
+    if (hId >= pb.H || n < pb.min_n || n < 1) return;
+    if (!pb.hyp_ok[hId]) return;
+    double tr[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) tr[j] = pb.hyp_tr[6 * hId + j];
+    Rot R;
+    make_rot(tr, R, false);
+    int cnt = 0;
+    for (int i = lane; i < n; i += 32) cnt += inlier_point(R, P, pb.X, pb.obs, pb.stride, i) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+    if (lane == 0) pb.hyp_count[hId] = cnt;
+}
+
+__constant__ int c_pair_a[27] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 0, 1, 2, 3, 4, 5};
+__constant__ int c_pair_b[27] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 6, 6, 6, 6, 6, 6};
+
+/*
+ * Block-cooperative minimize_reproj (viso.cpp:1583-1623) over an arbitrary active set.  Per iteration:
+ * all threads write Jacobian rows + residuals to `scratch` ([4*na][7]); lanes 0..26 of warp 0 then form the 21
+ * JtJ sums and 6 Jt*r sums SEQUENTIALLY in row order (bit-identical to cv::mulTransposed / the oracle's
+ * J^T r); thread 0 solves and decides.  tr_s: shared double[6], in/out.  Returns 1 converged / 0 failed.
+ */
+__device__ int gn_block(const double* __restrict__ X, const double* __restrict__ obs, int stride, int n,
+                        const int* __restrict__ active, int na, double* tr_s, const ParamDev& P,
+                        double* __restrict__ scratch, double* sums_s /* smem[27] */, int* flag_s /* smem */)
+{
+    for (int it = 0; it < 100; ++it) {
+        double tr[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) tr[j] = tr_s[j];
+        Rot R;
+        make_rot(tr, R, true);
+        for (int i = threadIdx.x; i < na; i += blockDim.x) {
+            const int a = active[i];
+            double ob[4], rows[4][7];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) ob[r] = obs[r * stride + a];
+            const double w = weight_of(P, obs[i]); /* column i, viso.cpp:1449 */
+            point_rows(R, P, X[a], X[stride + a], X[2 * stride + a], w, ob, rows);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 7; ++c) scratch[(size_t)(4 * i + r) * 7 + c] = rows[r][c];
+        }
+        __syncthreads();
+        if (threadIdx.x < 27) {
+            const int a = c_pair_a[threadIdx.x], b = c_pair_b[threadIdx.x];
+            double s = 0;
+            const int rowsN = 4 * na;
+#pragma unroll 4
+            for (int k = 0; k < rowsN; ++k) s += scratch[(size_t)k * 7 + a] * scratch[(size_t)k * 7 + b];
+            sums_s[threadIdx.x] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double A[6][6], b[6];
+            int t = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = a; c < 6; ++c) { A[a][c] = sums_s[t]; A[c][a] = sums_s[t]; ++t; }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) b[a] = sums_s[21 + a];
+            int flag;
+            if (!lu_solve6(A, b)) flag = 2;
+            else {
+                bool conv = true;
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    if (b[j] > P.thresh) { conv = false; break; }
+                if (conv) flag = 1;
+                else {
+                    flag = 0;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) tr_s[j] = tr_s[j] + b[j];
+                }
+            }
+            *flag_s = flag;
+        }
+        __syncthreads();
+        const int flag = *flag_s;
+        __syncthreads();
+        if (flag == 1) return 1;
+        if (flag == 2) return 0;
+    }
+    return 0;
+}
+
+/* ordered inlier list of `tr` over all n points (block cooperative); returns the count (same in all threads) */
+__device__ int inliers_block(const double* __restrict__ X, const double* __restrict__ obs, int stride, int n,
+                             const double* tr_s, const ParamDev& P, int* __restrict__ out, int* warp_tot)
+{
+    double tr[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) tr[j] = tr_s[j];
+    Rot R;
+    make_rot(tr, R, false);
+    int base = 0;
+    for (int start = 0; start < n; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        const bool flag = i < n && inlier_point(R, P, X, obs, stride, i);
+        const int slot = block_compact_slot(flag, base, warp_tot);
+        if (flag) out[slot] = i;
+    }
+    return base;
+}
+
+/* One CTA per problem: viso.cpp:1564-1579 */
+__global__ void __launch_bounds__(256) ransac_final_kernel(const RansacProb* __restrict__ probs, ParamDev P)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int best_cnt_s[256], best_idx_s[256];
+    __shared__ double tr_s[6];
+    __shared__ double sums_s[27];
+    __shared__ int flag_s;
+    const RansacProb& pb = probs[blockIdx.x];
+    const int n = *pb.n;
+    viso_record_dev* rec = pb.rec;
+    if (n < pb.min_n || n < 1) {
+        if (threadIdx.x == 0) {
+            for (int j = 0; j < 6; ++j) rec->tr[j] = pb.tr_init[j];
+            rec->ok = 0; rec->n_inliers = 0; rec->best_hyp = -1; rec->n_circ = n;
+        }
+        return;
+    }
+    /* first hypothesis with the strictly largest support (viso.cpp:1564: '>' against an initially empty set) */
+    int bc = 0, bi = INT_MAX;
+    for (int hId = threadIdx.x; hId < pb.H; hId += blockDim.x) {
+        if (pb.hyp_ok[hId]) {
+            const int c = pb.hyp_count[hId];
+            if (c > bc) { bc = c; bi = hId; }
+        }
+    }
+    best_cnt_s[threadIdx.x] = bc; best_idx_s[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const int c2 = best_cnt_s[threadIdx.x + o], i2 = best_idx_s[threadIdx.x + o];
+            if (c2 > best_cnt_s[threadIdx.x] || (c2 == best_cnt_s[threadIdx.x] && i2 < best_idx_s[threadIdx.x])) {
+                best_cnt_s[threadIdx.x] = c2; best_idx_s[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    const int best_cnt = best_cnt_s[0];
+    const int best_hyp = best_cnt > 0 ? best_idx_s[0] : -1;
+    if (threadIdx.x < 6) tr_s[threadIdx.x] = best_hyp >= 0 ? pb.hyp_tr[6 * best_hyp + threadIdx.x] : pb.tr_init[threadIdx.x];
+    __syncthreads();
+    int n_act = 0;
+    if (best_hyp >= 0) n_act = inliers_block(pb.X, pb.obs, pb.stride, n, tr_s, P, pb.active, warp_tot);
+    __syncthreads();
+    int ok = 0, n_inl = n_act;
+    const int* list = pb.active;
+    if (n_act >= 6) {
+        ok = gn_block(pb.X, pb.obs, pb.stride, n, pb.active, n_act, tr_s, P, pb.scratch, sums_s, &flag_s);
+        if (ok) {
+            n_inl = inliers_block(pb.X, pb.obs, pb.stride, n, tr_s, P, pb.inliers, warp_tot);
+            list = pb.inliers;
+        }
+    }
+    __syncthreads();
+    if (list != pb.inliers) /* failure: the reference leaves best_inliers = RANSAC support set */
+        for (int i = threadIdx.x; i < n_act; i += blockDim.x) pb.inliers[i] = pb.active[i];
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < 6; ++j) rec->tr[j] = tr_s[j];
+        rec->ok = ok; rec->n_inliers = n_inl; rec->best_hyp = best_hyp; rec->n_circ = n;
+    }
+}
+
+/* standalone minimize_reproj (viso_minimize_reproj): one CTA */
+__global__ void __launch_bounds__(256) gn_kernel(const double* X, const double* obs, int stride, const int* active,
+                                                 int na, double* tr, int* ok, double* scratch, ParamDev P)
+{
+    __shared__ double tr_s[6];
+    __shared__ double sums_s[27];
+    __shared__ int flag_s;
+    if (threadIdx.x < 6) tr_s[threadIdx.x] = tr[threadIdx.x];
+    __syncthreads();
+    const int r = gn_block(X, obs, stride, stride, active, na, tr_s, P, scratch, sums_s, &flag_s);
+    __syncthreads();
+    if (threadIdx.x < 6) tr[threadIdx.x] = tr_s[threadIdx.x];
+    if (threadIdx.x == 0) *ok = r;
+}
+
+/* standalone get_inliers (viso_get_inliers): one CTA */
+__global__ void __launch_bounds__(256) inliers_kernel(const double* X, const double* obs, int n, int stride,
+                                                      const double* tr, int* inliers, int* count, ParamDev P)
+{
+    __shared__ int warp_tot[32];
+    __shared__ double tr_s[6];
+    if (threadIdx.x < 6) tr_s[threadIdx.x] = tr[threadIdx.x];
+    __syncthreads();
+    const int c = inliers_block(X, obs, stride, n, tr_s, P, inliers, warp_tot);
+    if (threadIdx.x == 0) *count = c;
+}
+
+/* triangulate_rectified<double>, viso.cpp:1146-1152 */
+__global__ void triangulate_f64_kernel(const double* __restrict__ x, int m, int stride, double* __restrict__ X, ParamDev P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double u1 = x[i], v1 = x[stride + i], u2 = x[2 * stride + i];
+    const double d = u1 - u2;
+    X[i] = P.base * (u1 - P.cu) / d;
+    X[stride + i] = P.base * (v1 - P.cv) / d;
+    X[2 * stride + i] = P.f * P.base / d;
+}
+
+/* triangulate_rectified (float), mvg.cpp:184-190 */
+__global__ void triangulate_f32_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int m, double f,
+                                       double base, double c1u, double c1v, float* __restrict__ X)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double d = fmaxf(__fsub_rn(x1[i], x2[i]), 0.0001f);
+    X[i] = (float)((x1[i] - c1u) * base / d);
+    X[m + i] = (float)((x1[m + i] - c1v) * base / d);
+    X[2 * m + i] = (float)(f * base / d);
+}
+
+/* projectPoints, viso.cpp:326-333: x = h2e(P * e2h(X)); w == 0 raises the error flag (misc.h:118-119) */
+__global__ void project_kernel(const double* __restrict__ X, int n, const double* __restrict__ Pm, double* __restrict__ x,
+                               int* err)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double Xh[4] = {X[i], X[n + i], X[2 * n + i], 1.0};
+    double xh[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s += Pm[r * 4 + k] * Xh[k];
+        xh[r] = s;
+    }
+    if (fabs(xh[2]) == 0) { atomicOr(err, 4); return; }
+    x[i] = xh[0] / xh[2];
+    x[n + i] = xh[1] / xh[2];
+}
+
+/* ------------------------------------------------------------------------------------------------ launchers */
+
+cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dlen, int* err_flag, cudaStream_t s)
+{
+    if (n_jobs <= 0 || max_n <= 0) return cudaSuccess;
+    dim3 grid((max_n + 7) / 8, n_jobs);
+    pack_desc_kernel<<<grid, 256, 0, s>>>(jobs, dlen, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStream_t s)
+{
+    if (n_jobs <= 0) return cudaSuccess;
+    const size_t smem = (size_t)(2 * g.gx * g.gy + 1) * sizeof(int);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    grid_build_kernel<<<n_jobs, 512, smem, s>>>(jobs, g);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, const MatchParamsPair& mp, GridCfg g,
+                              unsigned long long* sad_pairs, cudaStream_t s)
+{
+    if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+    dim3 grid((max_nq + VISO_MATCH_QPC - 1) / VISO_MATCH_QPC, n_jobs);
+    sad_match_kernel<<<grid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, ParamDev p, cudaStream_t s)
+{
+    if (n_jobs <= 0) return cudaSuccess;
+    compact_sort_kernel<<<n_jobs, 256, 0, s>>>(jobs, p);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_circle(const CircleJob* jobs, int n_jobs, cudaStream_t s)
+{
+    if (n_jobs <= 0) return cudaSuccess;
+    circle_kernel<<<n_jobs, 256, 0, s>>>(jobs);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, int max_n, ParamDev p, cudaStream_t s,
+                               int* launches)
+{
+    if (n_probs <= 0 || max_H <= 0) return cudaSuccess;
+    ransac_hyp_kernel<<<dim3((max_H + 63) / 64, n_probs), 64, 0, s>>>(probs, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ransac_score_kernel<<<dim3((max_H + 7) / 8, n_probs), 256, 0, s>>>(probs, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ransac_final_kernel<<<n_probs, 256, 0, s>>>(probs, p);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_gn(const double* X, const double* obs, int stride, const int* active, int na, double* tr,
+                           int* ok, double* scratch, ParamDev p, cudaStream_t s)
+{
+    gn_kernel<<<1, 256, 0, s>>>(X, obs, stride, active, na, tr, ok, scratch, p);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_inliers(const double* X, const double* obs, int n, int stride, const double* tr, int* inliers,
+                                int* count, ParamDev p, cudaStream_t s)
+{
+    inliers_kernel<<<1, 256, 0, s>>>(X, obs, n, stride, tr, inliers, count, p);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_triangulate_f64(const double* x, int m, int stride, double* X, ParamDev p, cudaStream_t s)
+{
+    if (m <= 0) return cudaSuccess;
+    triangulate_f64_kernel<<<(m + 255) / 256, 256, 0, s>>>(x, m, stride, X, p);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_triangulate_f32(const float* x1, const float* x2, int m, double f, double base, double c1u,
+                                        double c1v, float* X, cudaStream_t s)
+{
+    if (m <= 0) return cudaSuccess;
+    triangulate_f32_kernel<<<(m + 255) / 256, 256, 0, s>>>(x1, x2, m, f, base, c1u, c1v, X);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_project(const double* X, int n, const double* P, double* x, int* err_flag, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    project_kernel<<<(n + 255) / 256, 256, 0, s>>>(X, n, P, x, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_circle_tables(const int* m, int n, int* table, int table_n, int key_col, int val_mode,
+                                      int* err_flag, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    circle_tables_kernel<<<(n + 255) / 256, 256, 0, s>>>(m, n, table, table_n, key_col, val_mode, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_circle_generic(const int* lr, int nlr, const int* lrp, int nlrp, const int* t11, int n_t11,
+                                       const int* tlrp, int n_tlrp, const int* t22, int n_t22,
+                                       int* circ4, int* pcl3, int* n_out, cudaStream_t s)
+{
+    circle_generic_kernel<<<1, 256, 0, s>>>(lr, nlr, lrp, nlrp, t11, n_t11, tlrp, n_tlrp, t22, n_t22, circ4, pcl3, n_out);
+    return cudaGetLastError();
+}

@@ -1,0 +1,152 @@
+/*
+ * viso_dev.h -- device-side data layout shared by kernels.cu and capi.cu (not part of the public ABI).
+ *
+ * HBM layout (see DESIGN.md "Data layout"):
+ *   keypoints        float2[n]                      original order (index = the reference's keypoint index)
+ *   descriptors f32  float[n][desc_len]             the reference's cv::Mat layout (input only)
+ *   descriptors u16  uint16[n][128]                 biased (v+1024) Sobel values; elements 126..127 hold the
+ *                                                   32-bit row sum; 256 B per row = 16 x uint4
+ *   candidate grid   cell_start int[ncell+1], sxy float2[n], sidx int[n]   counting sort by 16-px cell
+ *   dense match out  int4[n]                        (best_idx, best_d1, best_d2, valid) per query
+ */
+#ifndef VISO_DEV_H_
+#define VISO_DEV_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define VISO_DESC_U16 128
+#define VISO_GRID_CS 16          /* candidate grid cell size in pixels (power of two: exact float scaling) */
+#define VISO_HIST_BINS 128
+#define VISO_TIE_CAP 64
+#define VISO_MATCH_WARPS 8
+#define VISO_MATCH_QPC 32        /* queries per CTA in sad_match */
+
+struct GridCfg { int gx, gy; };
+
+struct SetView {
+    const float2* xy;        /* original order */
+    const int* n;            /* device pointer to the keypoint count */
+    const uint16_t* desc;    /* packed rows */
+    const float2* sxy;       /* cell-sorted coordinates */
+    const int* sidx;         /* cell-sorted -> original index */
+    const int* cell_start;   /* ncell+1 */
+};
+
+struct MatchParamsDev {
+    float radius;
+    int K;
+    int epipolar;
+    int second_best;
+    double sampson_thresh;
+    double ratio;
+    double F[9];
+};
+
+struct MatchParamsPair { MatchParamsDev p[2]; };
+
+struct MatchJob {
+    SetView q, t;
+    int4* out;               /* dense per query, indexed by original query index */
+    int mode;                /* index into MatchParamsPair */
+    int pad;
+};
+
+struct PackJob {
+    const float* d;          /* n x dlen float */
+    const int* n;
+    uint16_t* out;           /* n x 128 u16 */
+};
+
+struct GridJob {
+    const float2* xy;
+    const int* n;
+    float2* sxy;
+    int* sidx;
+    int* cell_start;
+};
+
+struct ParamDev {
+    double base, f, cu, cv, thr2, thresh;
+    int H;
+    int pad;
+};
+
+/* one RANSAC problem (a frame pair, or a standalone call): 3 x n points, 4 x n observations, row stride `stride` */
+struct RansacProb {
+    const double* X;         /* rows at X + r*stride */
+    const double* obs;
+    const int* n;            /* device pointer to the correspondence count */
+    int stride;
+    int H;
+    const uint32_t* seeds;   /* [H][3] or null */
+    const int* table;        /* [H][3] explicit sample table or null (then derived from seeds) */
+    double* hyp_tr;          /* [H][6] */
+    int* hyp_ok;             /* [H] */
+    int* hyp_count;          /* [H] */
+    double* scratch;         /* [stride*4][7] doubles: Jacobian rows + residual for the refine */
+    int* inliers;            /* [stride] */
+    int* active;             /* [stride] scratch: RANSAC support set */
+    struct viso_record_dev* rec;
+    double tr_init[6];       /* caller's best_tr (kept when no hypothesis succeeds) */
+    int min_n;               /* problems with n < min_n are skipped (3 in the pipeline, viso.cpp:1283) */
+    int pad;
+};
+
+struct viso_record_dev {
+    double tr[6];
+    int ok, n_inliers, n_circ, best_hyp;
+};
+
+struct SortJob {               /* per frame: compaction + reference sort order + collect + triangulate */
+    const int4* dense;         /* stereo dense result */
+    const int* n;              /* queries (left keypoints) */
+    const float2* kp1;
+    const float2* kp2;
+    int* matches;              /* [cap][3] */
+    int* count;                /* out */
+    int* pos_of_query;         /* [cap] position in sorted order or -1 */
+    double* x;                 /* 4 x stride */
+    double* X;                 /* 3 x stride */
+    int stride;
+    int pad;
+};
+
+struct CircleJob {             /* per frame pair */
+    const int* lr; const int* lr_count;          /* match_lr (cur) */
+    const int* lrp; const int* lrp_count;        /* match_lr_prev */
+    const int* pos_prev;                         /* pos_of_query of previous frame */
+    const int* n_prev_left;                      /* bound for pos_prev lookups */
+    const int4* m11; const int4* m22;            /* temporal dense results (cur queries) */
+    const double* x; const double* Xp;           /* x of cur (4 x stride), X of prev (3 x stride) */
+    int* circ4; int* pcl2; int* n_circ;
+    double* x_c; double* Xp_c;                   /* 4 x stride, 3 x stride */
+    viso_record_dev* rec;
+    int stride;
+    int pad;
+};
+
+/* launch wrappers (kernels.cu).  All enqueue on `s` and return cudaGetLastError(). */
+cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dlen, int* err_flag, cudaStream_t s);
+cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStream_t s);
+cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, const MatchParamsPair& mp, GridCfg g,
+                              unsigned long long* sad_pairs, cudaStream_t s);
+cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, ParamDev p, cudaStream_t s);
+cudaError_t viso_launch_circle(const CircleJob* jobs, int n_jobs, cudaStream_t s);
+cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, int max_n, ParamDev p, cudaStream_t s,
+                               int* launches);
+cudaError_t viso_launch_gn(const double* X, const double* obs, int stride, const int* active, int na, double* tr,
+                           int* ok, double* scratch, ParamDev p, cudaStream_t s);
+cudaError_t viso_launch_inliers(const double* X, const double* obs, int n, int stride, const double* tr, int* inliers,
+                                int* count, ParamDev p, cudaStream_t s);
+cudaError_t viso_launch_triangulate_f64(const double* x, int m, int stride, double* X, ParamDev p, cudaStream_t s);
+cudaError_t viso_launch_triangulate_f32(const float* x1, const float* x2, int m, double f, double base, double c1u,
+                                        double c1v, float* X, cudaStream_t s);
+cudaError_t viso_launch_project(const double* X, int n, const double* P, double* x, int* err_flag, cudaStream_t s);
+cudaError_t viso_launch_circle_tables(const int* m, int n, int* table, int table_n, int key_col, int val_mode,
+                                      int* err_flag, cudaStream_t s);
+cudaError_t viso_launch_circle_generic(const int* lr, int nlr, const int* lrp, int nlrp, const int* t11, int n_t11,
+                                       const int* tlrp, int n_tlrp, const int* t22, int n_t22,
+                                       int* circ4, int* pcl3, int* n_out, cudaStream_t s);
+
+#endif
