@@ -13,9 +13,9 @@
  * fallback: without a CUDA device viso_create() fails and nothing else can be called.
  *
  * Domain restrictions (checked on the device, VISO_ERR_DOMAIN when violated):
- *   - descriptors must be integer valued with |v| <= 1023 and desc_len <= 128 (the reference's descriptors are
+ *   - descriptors must be integer valued with |v| <= 1023 and desc_len <= 126 (the reference's descriptors are
  *     3x3 Sobel-x responses of 8-bit images, |v| <= 1020, 121 per keypoint: viso.cpp:999-1002,1010);
- *   - 1 <= max_neighbors <= 1024.
+ *   - max_neighbors >= 1.
  */
 #ifndef VISO_B200_H_
 #define VISO_B200_H_
@@ -87,6 +87,10 @@ int viso_sync(viso_ctx* ctx);
 int viso_set_image_extent(viso_ctx* ctx, int width, int height);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 int64_t viso_launch_count(const viso_ctx* ctx);
+/* CUDA-event stopwatch on the context stream: begin records an event; end records a second one, waits for it and
+ * returns the elapsed milliseconds of everything enqueued in between */
+int viso_timer_begin(viso_ctx* ctx);
+int viso_timer_end(viso_ctx* ctx, float* ms);
 
 void viso_match_params_stereo(viso_match_params* p, const double F[9]); /* MatchParams(Mat F), viso.cpp:62-71 */
 void viso_match_params_temporal(viso_match_params* p);                  /* MatchParams(), viso.cpp:72-74 */

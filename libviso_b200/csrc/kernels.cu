@@ -1099,6 +1099,26 @@ __global__ void project_kernel(const double* __restrict__ X, int n, const double
     x[n + i] = xh[1] / xh[2];
 }
 
+/* collect_matches (Mat x, 4 x m), viso.cpp:501-514, + triangulate_rectified<double>, viso.cpp:1146-1152 */
+__global__ void collect_tri_kernel(const float2* __restrict__ kp1, int n1, const float2* __restrict__ kp2, int n2,
+                                   const int* __restrict__ matches, int m, double* __restrict__ x, double* __restrict__ X,
+                                   ParamDev P, int* err)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    const int i1 = matches[3 * p], i2 = matches[3 * p + 1];
+    if (i1 < 0 || i1 >= n1 || i2 < 0 || i2 >= n2) { atomicOr(err, 8); return; }
+    const float2 a = kp1[i1], b = kp2[i2];
+    const double u1 = a.x, v1 = a.y, u2 = b.x, v2 = b.y;
+    if (x) { x[p] = u1; x[m + p] = v1; x[2 * m + p] = u2; x[3 * m + p] = v2; }
+    if (X) {
+        const double d = u1 - u2;
+        X[p] = P.base * (u1 - P.cu) / d;
+        X[m + p] = P.base * (v1 - P.cv) / d;
+        X[2 * m + p] = P.f * P.base / d;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ launchers */
 
 cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dlen, int* err_flag, cudaStream_t s)
@@ -1208,5 +1228,13 @@ cudaError_t viso_launch_circle_generic(const int* lr, int nlr, const int* lrp, i
                                        int* circ4, int* pcl3, int* n_out, cudaStream_t s)
 {
     circle_generic_kernel<<<1, 256, 0, s>>>(lr, nlr, lrp, nlrp, t11, n_t11, tlrp, n_tlrp, t22, n_t22, circ4, pcl3, n_out);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_collect_tri(const float2* kp1, int n1, const float2* kp2, int n2, const int* matches, int m,
+                                    double* x, double* X, ParamDev p, int* err_flag, cudaStream_t s)
+{
+    if (m <= 0) return cudaSuccess;
+    collect_tri_kernel<<<(m + 255) / 256, 256, 0, s>>>(kp1, n1, kp2, n2, matches, m, x, X, p, err_flag);
     return cudaGetLastError();
 }

@@ -148,5 +148,7 @@ cudaError_t viso_launch_circle_tables(const int* m, int n, int* table, int table
 cudaError_t viso_launch_circle_generic(const int* lr, int nlr, const int* lrp, int nlrp, const int* t11, int n_t11,
                                        const int* tlrp, int n_tlrp, const int* t22, int n_t22,
                                        int* circ4, int* pcl3, int* n_out, cudaStream_t s);
+cudaError_t viso_launch_collect_tri(const float2* kp1, int n1, const float2* kp2, int n2, const int* matches, int m,
+                                    double* x, double* X, ParamDev p, int* err_flag, cudaStream_t s);
 
 #endif

@@ -1,0 +1,390 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Integer / index work (match indices, SAD distances, match order, circular matches, inlier sets, per-hypothesis
+support counts) must be bit-exact.  Floating point: tr vectors of the RANSAC hypotheses and of the refined pose are
+compared with TR_TOL (rotations, rad) and REL_T_TOL (relative translation) -- device sin/cos may differ from glibc
+in the last place, everything else is evaluated with the reference's operation order (-fmad=false).
+"""
+import numpy as np
+import pytest
+
+from conftest import make_seeds
+
+pytestmark = pytest.mark.gpu
+
+TR_TOL = 1e-6      # rad, north_star
+REL_T_TOL = 1e-6   # relative translation, north_star
+
+
+def assert_tr_close(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.all(np.abs(a[..., :3] - b[..., :3]) <= TR_TOL), (a, b)
+    scale = np.maximum(np.linalg.norm(b[..., 3:], axis=-1, keepdims=True), 1e-3)
+    assert np.all(np.abs(a[..., 3:] - b[..., 3:]) <= REL_T_TOL * scale), (a, b)
+
+
+def dense_equal(g, o):
+    for k in ("idx", "d1", "d2", "valid"):
+        assert np.array_equal(g[k], o[k]), k
+
+
+def random_features(rng, n, w=1241, h=376, dlen=121, integer=True):
+    if integer:
+        flat = rng.choice(w * h, n, replace=False)
+        kp = np.stack([flat % w, flat // w], 1).astype(np.float32)
+    else:
+        kp = (rng.random((n, 2)) * [w, h]).astype(np.float32)
+    d = rng.integers(-1020, 1021, size=(n, dlen)).astype(np.float32)
+    return kp, d
+
+
+# ------------------------------------------------------------------------------------------------ match_desc
+
+@pytest.mark.parametrize("mode", ["stereo", "temporal"])
+def test_match_desc_synthetic_frames(ctx, api, oracle, small_sequence, mode):
+    from libviso_b200 import synth
+    frames, _ = small_sequence
+    P1, P2 = synth.kitti_calib()
+    F = oracle.F_from_P(P1, P2)
+    for t in (1, 3):
+        f, fp = frames[t], frames[t - 1]
+        if mode == "stereo":
+            args = (f["kpL"], f["kpR"], f["dL"], f["dR"])
+            so, sg = oracle.match_params_stereo(F), api.match_params_stereo(F)
+        else:
+            args = (f["kpL"], fp["kpL"], f["dL"], fp["dL"])
+            so, sg = oracle.match_params_temporal(), api.match_params_temporal()
+        o = oracle.match_desc(*args, so)
+        dense_equal(ctx.match_desc_dense(*args, sg), o)
+        assert np.array_equal(ctx.match_desc(*args, sg), o["matches"])
+        assert len(o["matches"]) > 50
+
+
+@pytest.mark.parametrize("n,K,radius,integer", [
+    (3000, 250, 80.0, True),     # top-K truncation binds for most queries (dense), many L1 ties
+    (3000, 16, 80.0, True),      # tiny K: threshold refinement inside a distance bin
+    (1500, 200, 80.0, False),    # float coordinates: real (dist, idx) selection
+    (800, 5, 300.0, True),       # radius larger than the image height
+    (500, 250, 0.0, True),       # radius 0: only coincident points
+    (400, 1, 40.0, True),
+])
+def test_match_desc_random(ctx, api, oracle, n, K, radius, integer):
+    rng = np.random.default_rng(n * 7 + K)
+    w, h = (400, 300) if n >= 1500 else (1241, 376)
+    kp1, d1 = random_features(rng, n, w, h, integer=integer)
+    kp2, d2 = random_features(rng, n + 17, w, h, integer=integer)
+    if radius == 0.0:
+        kp2[5:200] = kp1[5:200]
+    # make SAD ties likely: copy some descriptors
+    d2[rng.integers(0, len(d2), 300)] = d2[rng.integers(0, len(d2), 300)]
+    for second in (0, 1):
+        so = oracle.match_params_temporal(); sg = api.match_params_temporal()
+        for s in (so, sg):
+            s.max_neighbors = K; s.radius = radius; s.enforce_2nd_best = second
+        o = oracle.match_desc(kp1, kp2, d1, d2, so)
+        dense_equal(ctx.match_desc_dense(kp1, kp2, d1, d2, sg), o)
+        assert np.array_equal(ctx.match_desc(kp1, kp2, d1, d2, sg), o["matches"])
+
+
+def test_match_desc_index0_terminator(ctx, api, oracle):
+    """target index 0 ends the reference's candidate scan (viso.cpp:693): put it in the middle of the image"""
+    rng = np.random.default_rng(5)
+    kp1, d1 = random_features(rng, 1200, 300, 200)
+    kp2, d2 = random_features(rng, 1200, 300, 200)
+    kp2[0] = (150, 100)
+    so, sg = oracle.match_params_temporal(), api.match_params_temporal()
+    o = oracle.match_desc(kp1, kp2, d1, d2, so)
+    assert (o["idx"] == -1).sum() > 0 and (o["idx"] == 0).sum() == 0
+    dense_equal(ctx.match_desc_dense(kp1, kp2, d1, d2, sg), o)
+
+
+def test_match_desc_duplicate_points_and_identical_descriptors(ctx, api, oracle):
+    """coincident keypoints (L1 ties broken by index) and identical descriptors (SAD ties -> last in scan order)"""
+    rng = np.random.default_rng(6)
+    base, d = random_features(rng, 60, 200, 120)
+    kp2 = np.repeat(base, 8, axis=0); d2 = np.repeat(d, 8, axis=0)
+    kp1, d1 = random_features(rng, 300, 200, 120)
+    d1[:50] = d[:50]
+    for K in (7, 64, 250):
+        so, sg = oracle.match_params_temporal(), api.match_params_temporal()
+        so.max_neighbors = sg.max_neighbors = K
+        o = oracle.match_desc(kp1, kp2, d1, d2, so)
+        dense_equal(ctx.match_desc_dense(kp1, kp2, d1, d2, sg), o)
+        assert np.array_equal(ctx.match_desc(kp1, kp2, d1, d2, sg), o["matches"])
+
+
+def test_match_desc_epipolar_gate_general_F(ctx, api, oracle):
+    rng = np.random.default_rng(8)
+    kp1, d1 = random_features(rng, 1500, 640, 300)
+    kp2, d2 = random_features(rng, 1500, 640, 300)
+    F = np.array([[1e-7, 2e-6, -3e-4], [-1e-6, 2e-7, 4e-2], [2e-4, -4.1e-2, 1.0]])
+    so, sg = oracle.match_params_stereo(F), api.match_params_stereo(F)
+    so.sampson_thresh = sg.sampson_thresh = 4.0
+    o = oracle.match_desc(kp1, kp2, d1, d2, so)
+    assert o["valid"].sum() > 100
+    dense_equal(ctx.match_desc_dense(kp1, kp2, d1, d2, sg), o)
+    # degenerate F: every Sampson distance is NaN -> nothing matches
+    so, sg = oracle.match_params_stereo(np.zeros((3, 3))), api.match_params_stereo(np.zeros((3, 3)))
+    o = oracle.match_desc(kp1, kp2, d1, d2, so)
+    assert o["valid"].sum() == 0
+    dense_equal(ctx.match_desc_dense(kp1, kp2, d1, d2, sg), o)
+
+
+def test_match_desc_empty_and_ragged(ctx, api, oracle):
+    rng = np.random.default_rng(9)
+    kp, d = random_features(rng, 40)
+    sg = api.match_params_temporal(); so = oracle.match_params_temporal()
+    e_kp = np.zeros((0, 2), np.float32); e_d = np.zeros((0, 121), np.float32)
+    assert len(ctx.match_desc(e_kp, kp, e_d, d, sg)) == 0
+    g = ctx.match_desc_dense(kp, e_kp, d, e_d, sg)
+    assert (g["idx"] == -1).all() and (g["valid"] == 0).all()
+    assert len(ctx.match_desc(kp, e_kp, d, e_d, sg)) == 0
+    # one target only: it is index 0, the terminator, so never matched
+    g = ctx.match_desc_dense(kp, kp[:1], d, d[:1], sg)
+    dense_equal(g, oracle.match_desc(kp, kp[:1], d, d[:1], so))
+    # short descriptors and keypoints far outside the default image extent
+    kp1, d1 = random_features(rng, 300, 3000, 2000, dlen=9)
+    kp2, d2 = random_features(rng, 333, 3000, 2000, dlen=9)
+    kp1[:10] -= 500
+    dense_equal(ctx.match_desc_dense(kp1, kp2, d1, d2, sg), oracle.match_desc(kp1, kp2, d1, d2, so))
+
+
+def test_match_desc_domain_errors(ctx, api):
+    rng = np.random.default_rng(10)
+    kp, d = random_features(rng, 40)
+    sg = api.match_params_temporal()
+    bad = d.copy(); bad[3, 7] = 0.5
+    with pytest.raises(api.VisoError) as e:
+        ctx.match_desc(kp, kp, bad, d, sg)
+    assert e.value.code == -3
+    bad = d.copy(); bad[3, 7] = 5000
+    with pytest.raises(api.VisoError):
+        ctx.match_desc(kp, kp, d, bad, sg)
+    sg.max_neighbors = 0
+    with pytest.raises(api.VisoError):
+        ctx.match_desc(kp, kp, d, d, sg)
+
+
+def test_match_desc_20k_properties(ctx, api, oracle):
+    """BASELINE config 3 size (20k keypoints / image).  Full oracle comparison on a query subset (the oracle's scan
+    is per query, so a subset of queries against the full target set is exact), plus size-independent properties."""
+    from libviso_b200 import synth
+    pair = synth.make_dense_pair(20000, seed=2000)
+    P1, P2 = synth.kitti_calib()
+    F = oracle.F_from_P(P1, P2)
+    for name, so, sg in (("stereo", oracle.match_params_stereo(F), api.match_params_stereo(F)),
+                         ("temporal", oracle.match_params_temporal(), api.match_params_temporal())):
+        g = ctx.match_desc_dense(pair["kpL"], pair["kpR"], pair["dL"], pair["dR"], sg)
+        sub = np.random.default_rng(1).choice(20000, 400, replace=False)
+        o = oracle.match_desc(pair["kpL"][sub], pair["kpR"], pair["dL"][sub], pair["dR"], so)
+        for k in ("idx", "d1", "d2", "valid"):
+            assert np.array_equal(g[k][sub], o[k]), (name, k)
+        v = g["valid"] == 1
+        # properties: the reported distance is the SAD of the reported pair; the pair is within the radius; index 0
+        # is never matched; d1 <= d2
+        sad = np.abs(pair["dL"][v] - pair["dR"][g["idx"][v]]).sum(1).astype(np.int64)
+        assert np.array_equal(sad, g["d1"][v])
+        l1 = np.abs(pair["kpL"][v] - pair["kpR"][g["idx"][v]]).sum(1)
+        assert (l1 <= 80).all() and (g["idx"][v] > 0).all() and (g["d1"] <= g["d2"]).all()
+        m = ctx.match_desc(pair["kpL"], pair["kpR"], pair["dL"], pair["dR"], sg)
+        assert len(m) == v.sum() and (np.diff(m[:, 2]) >= 0).all()
+        assert np.array_equal(np.sort(m[:, 0]), np.nonzero(v)[0])
+        assert np.array_equal(m, oracle.sort_matches(np.stack([np.nonzero(v)[0], g["idx"][v], g["d1"][v]], 1)))
+
+
+# ------------------------------------------------------------------------------------------------ circle / geometry
+
+def test_match_circle(ctx, oracle, small_sequence):
+    from libviso_b200 import synth
+    frames, _ = small_sequence
+    P1, P2 = synth.kitti_calib()
+    F = oracle.F_from_P(P1, P2)
+    f, fp = frames[2], frames[1]
+    mlr = oracle.match_desc(f["kpL"], f["kpR"], f["dL"], f["dR"], oracle.match_params_stereo(F))["matches"]
+    mlrp = oracle.match_desc(fp["kpL"], fp["kpR"], fp["dL"], fp["dR"], oracle.match_params_stereo(F))["matches"]
+    m11 = oracle.match_desc(f["kpL"], fp["kpL"], f["dL"], fp["dL"], oracle.match_params_temporal())["matches"]
+    m22 = oracle.match_desc(f["kpR"], fp["kpR"], f["dR"], fp["dR"], oracle.match_params_temporal())["matches"]
+    co, po = oracle.match_circle(mlr, mlrp, m11, m22)
+    cg, pg = ctx.match_circle(mlr, mlrp, m11, m22)
+    assert len(co) > 20
+    assert np.array_equal(cg, co) and np.array_equal(pg, po)
+    e = np.zeros((0, 3), np.int32)
+    assert len(ctx.match_circle(e, mlrp, m11, m22)[0]) == 0
+    assert len(ctx.match_circle(mlr, mlrp, e, m22)[0]) == 0
+
+
+def test_match_circle_rejects_duplicates(ctx, api):
+    m = np.array([[0, 1, 5], [1, 2, 6]], np.int32)
+    dup = np.array([[0, 1, 5], [0, 2, 6]], np.int32)
+    with pytest.raises(api.VisoError) as e:
+        ctx.match_circle(m, m, dup, m)
+    assert e.value.code == -5
+
+
+def test_triangulate_and_project(ctx, oracle):
+    from libviso_b200 import synth
+    rng = np.random.default_rng(11)
+    m = 5000
+    x = np.stack([rng.uniform(0, 1241, m), rng.uniform(0, 376, m), rng.uniform(0, 1241, m), rng.uniform(0, 376, m)])
+    x[2, :10] = x[0, :10]            # zero disparity -> inf/nan exactly like the reference (no clamp)
+    x = np.round(x)                  # integer pixels as produced by the detector
+    Xg = ctx.triangulate_rectified_f64(x, synth.F_PX, synth.BASE, synth.CU, synth.CV)
+    Xo = oracle.triangulate_rectified_f64(x, synth.F_PX, synth.BASE, synth.CU, synth.CV)
+    assert np.array_equal(Xg, Xo, equal_nan=True)
+    x1 = x[:2].astype(np.float32); x2 = x[2:].astype(np.float32)
+    Xg = ctx.triangulate_rectified_f32(x1, x2, synth.F_PX, synth.BASE, synth.CU, synth.CV)
+    Xo = oracle.triangulate_rectified_f32(x1, x2, synth.F_PX, synth.BASE, synth.CU, synth.CV)
+    assert np.array_equal(Xg, Xo)
+    P1, P2 = synth.kitti_calib()
+    X = np.stack([rng.uniform(-20, 20, m), rng.uniform(-2, 3, m), rng.uniform(4, 60, m)])
+    assert np.array_equal(ctx.project_points(X, P2), oracle.project_points(X, P2))
+    X[2, 7] = 0.0
+    with pytest.raises(OverflowError):
+        ctx.project_points(X, P1)
+    with pytest.raises(OverflowError):
+        oracle.project_points(X, P1)
+    # collect_matches + triangulate fused
+    kp1 = np.round(rng.uniform(0, 1241, (300, 2))).astype(np.float32)
+    kp2 = np.round(rng.uniform(0, 1241, (310, 2))).astype(np.float32)
+    mt = np.stack([rng.integers(0, 300, 200), rng.integers(0, 310, 200), rng.integers(0, 9999, 200)], 1).astype(np.int32)
+    xg, Xg = ctx.collect_triangulate(kp1, kp2, mt, synth.F_PX, synth.BASE, synth.CU, synth.CV)
+    xo = oracle.collect_matches(kp1, kp2, mt)
+    assert np.array_equal(xg, xo)
+    assert np.array_equal(Xg, oracle.triangulate_rectified_f64(xo, synth.F_PX, synth.BASE, synth.CU, synth.CV),
+                          equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------ estimation
+
+def _params(api, oracle, H):
+    from libviso_b200 import synth
+    kw = dict(base=synth.BASE, f=synth.F_PX, cu=synth.CU, cv=synth.CV, ransac_iter=H)
+    return api.param_default(**kw), oracle.param_default(**kw)
+
+
+def test_get_inliers_and_minimize_reproj(ctx, api, oracle):
+    from libviso_b200 import synth
+    X, obs, tr_true = synth.make_ransac_problem(2000, seed=3001)
+    pg, po = _params(api, oracle, 50)
+    for tr in (np.zeros(6), tr_true, tr_true + 0.01):
+        io, _, margin = oracle.get_inliers(X, obs, tr, po)
+        ig = ctx.get_inliers(X, obs, tr, pg)
+        assert margin > 1e-9, "fixture is knife-edge"
+        assert np.array_equal(ig, io)
+    # the reference's disabled known-answer recipe (test/test.cpp:51-114): noise-free points, GN from 0
+    rng = np.random.default_rng(1)
+    Xk = np.stack([rng.uniform(-10, 10, 10), rng.uniform(-2, 2, 10), rng.uniform(5, 40, 10)])
+    tr0 = np.array([0, 0, 0, 1.0, 0, 0])
+    T = oracle.tr2mat(tr0)
+    Xc = T[:3, :3] @ Xk + T[:3, 3:]
+    ob = np.stack([synth.F_PX * Xc[0] / Xc[2] + synth.CU, synth.F_PX * Xc[1] / Xc[2] + synth.CV,
+                   synth.F_PX * (Xc[0] - synth.BASE) / Xc[2] + synth.CU, synth.F_PX * Xc[1] / Xc[2] + synth.CV])
+    act = np.arange(10, dtype=np.int32)
+    ok_o, tr_o, _ = oracle.minimize_reproj(Xk, ob, np.zeros(6), po, act)
+    ok_g, tr_g = ctx.minimize_reproj(Xk, ob, np.zeros(6), pg, act)
+    assert ok_o and ok_g and np.abs(tr_o - tr0).sum() < 1e-4 and np.abs(tr_g - tr0).sum() < 1e-4
+    assert_tr_close(tr_g, tr_o)
+    # noisy subset with a non-trivial active list (exercises the observe(0,i) weight quirk, viso.cpp:1449)
+    act = np.sort(rng.choice(2000, 700, replace=False)).astype(np.int32)
+    io, _, _ = oracle.get_inliers(X, obs, tr_true, po)
+    act = np.intersect1d(act, io).astype(np.int32)
+    ok_o, tr_o, it = oracle.minimize_reproj(X, obs, tr_true * 0.9, po, act)
+    ok_g, tr_g = ctx.minimize_reproj(X, obs, tr_true * 0.9, pg, act)
+    assert ok_o == ok_g
+    assert_tr_close(tr_g, tr_o)
+    # singular: all three points identical -> solve fails -> false, tr untouched
+    act = np.array([5, 5, 5], np.int32)
+    ok_o, tr_o, _ = oracle.minimize_reproj(X, obs, np.zeros(6), po, act)
+    ok_g, tr_g = ctx.minimize_reproj(X, obs, np.zeros(6), pg, act)
+    assert ok_o == ok_g
+    assert_tr_close(tr_g, tr_o)
+
+
+@pytest.mark.parametrize("n,H", [(400, 50), (10000, 256)])
+def test_ransac_minimize_reproj(ctx, api, oracle, n, H):
+    from libviso_b200 import synth
+    X, obs, tr_true = synth.make_ransac_problem(n, seed=3000 + n)
+    pg, po = _params(api, oracle, H)
+    table = oracle.randomsample_table(424242, H, n)
+    o = oracle.ransac_minimize_reproj(X, obs, po, table)
+    g = ctx.ransac_minimize_reproj(X, obs, pg, table)
+    assert o["ok"] and g["ok"]
+    assert np.array_equal(g["hyp_ok"], o["hyp_ok"])
+    assert np.array_equal(g["hyp_count"], o["hyp_count"])
+    okm = o["hyp_ok"] == 1
+    assert_tr_close(g["hyp_tr"][okm], o["hyp_tr"][okm])
+    assert g["best_hyp"] == o["best_hyp"]
+    assert np.array_equal(g["inliers"], o["inliers"])
+    assert_tr_close(g["tr"], o["tr"])
+    assert np.abs(g["tr"] - tr_true).max() < 0.05
+
+
+def test_ransac_failure_modes(ctx, api, oracle):
+    from libviso_b200 import synth
+    rng = np.random.default_rng(2)
+    pg, po = _params(api, oracle, 20)
+    # pure noise: fewer than 6 inliers for every hypothesis -> false, best_tr = winning hypothesis (or the input)
+    n = 60
+    X = np.stack([rng.uniform(-20, 20, n), rng.uniform(-2, 3, n), rng.uniform(4, 60, n)])
+    obs = np.stack([rng.uniform(0, 1241, n), rng.uniform(0, 376, n), rng.uniform(0, 1241, n), rng.uniform(0, 376, n)])
+    table = oracle.randomsample_table(7, 20, n)
+    tr0 = np.array([0.1, 0.2, 0.3, 1, 2, 3.0])
+    o = oracle.ransac_minimize_reproj(X, obs, po, table, tr0)
+    g = ctx.ransac_minimize_reproj(X, obs, pg, table, tr0)
+    assert not o["ok"] and not g["ok"]
+    assert np.array_equal(g["hyp_ok"], o["hyp_ok"]) and np.array_equal(g["hyp_count"], o["hyp_count"])
+    assert g["best_hyp"] == o["best_hyp"] and np.array_equal(g["inliers"], o["inliers"])
+    assert_tr_close(g["tr"], o["tr"])
+    # fewer than 3 correspondences: nothing to sample
+    g = ctx.ransac_minimize_reproj(X[:, :2], obs[:, :2], pg, table, tr0)
+    assert not g["ok"] and np.array_equal(g["tr"], tr0)
+
+
+# ------------------------------------------------------------------------------------------------ whole sequence
+
+def test_sequence_pipeline(ctx, api, oracle, small_sequence):
+    """viso.cpp:1205-1327 over 6 frames: every intermediate product is compared"""
+    from libviso_b200 import synth
+    frames, gt = small_sequence
+    frames = [dict(f) for f in frames]
+    # ragged input: one frame with far fewer keypoints, one empty right image
+    frames[4] = {k: v[:150] for k, v in frames[4].items()}
+    frames[5]["kpR"] = frames[5]["kpR"][:0]
+    frames[5]["dR"] = frames[5]["dR"][:0]
+    nF, H = len(frames), 50
+    P1, P2 = synth.kitti_calib()
+    seeds = make_seeds(nF, H)
+    po = oracle.param_default(ransac_iter=H)
+    pg = api.param_default(ransac_iter=H)
+    o = oracle.sequence(frames, P1, P2, po, seeds, dump=True)
+    seq = ctx.sequence(nF, 640, 121, H)
+    seq.set_calib(P1, P2)
+    seq.upload(frames)
+    seq.run(pg, seeds)
+    rec = seq.download()
+    for t in range(nF):
+        assert np.array_equal(seq.get_lr_matches(t), o["lr_matches"][t]), t
+        if t == 0:
+            continue
+        assert np.array_equal(seq.get_dense(1, t), o["m11"][t]), t
+        assert np.array_equal(seq.get_dense(2, t), o["m22"][t]), t
+        c4, _ = seq.get_circ(t)
+        assert np.array_equal(c4, o["circ"][t]), t
+        assert np.array_equal(seq.get_inliers(t), o["inliers"][t]), t
+    for k in ("ok", "n_inliers", "n_circ", "best_hyp"):
+        assert np.array_equal(rec[k], o["records"][k]), k
+    assert_tr_close(rec["tr"], o["records"]["tr"])
+    assert rec["ok"][1:4].all()
+    poses = api.chain_poses(rec)
+    assert len(poses) == len(o["poses"])
+    assert np.abs(poses - o["poses"]).max() < 1e-6
+    # the estimated motion is the ground-truth motion of the synthetic scene (sanity, loose)
+    for t in (1, 2, 3):
+        assert np.abs(api.tr2mat(rec["tr"][t]) - gt[t]).max() < 0.05
+    # idempotence: a second run over the resident inputs reproduces the records bit for bit
+    seq.run(pg)
+    rec2 = seq.download()
+    assert rec2.tobytes() == rec.tobytes()
+    mb, pairs = seq.stats()
+    assert mb > 0 and pairs > 0
+    seq.close()
