@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/s of the libviso hot path (match + circle + triangulate + RANSAC/GN pose) on B200.
+
+A "step" is one pass of the whole per-frame loop of sequence_odometry (reference src/viso.cpp:1205-1327, minus
+detection / description / debug output) over one synthetic KITTI-shaped 1241x376 stereo sequence of --frames frames
+(BASELINE.json configs[1]: 1000 frames, ~2k features per image, 50 RANSAC hypotheses per frame pair).
+
+  value  device throughput: features already resident in HBM (the reference's f32 cv::Mat descriptor layout + keypoints)
+         when the timed region starts; K steps timed with CUDA events on the library's stream
+  e2e    the same through the C-ABI with HOST buffers: every step copies all frames' keypoints + descriptors + sample
+         seeds from pinned host memory and reads the 64-byte records back
+  roofline   the sad_match kernel: algorithmic bytes (per frame pair, u16 layout) / its CUDA-event time
+  cpu_baseline   the CPU oracle (restated reference path, 1 thread) on a bounded sample of the same sequence
+
+Multi-GPU: one process per GPU (torchrun), each rank owns one independent sequence (seed 1000+rank) -- frame pairs
+and sequences are independent, so there is no data-path collective; the per-frame-pair records are gathered to
+rank 0 over NCCL and chained into poses there.  Weak scaling.
+
+`--impl reference` times the reference's CPU path (the oracle port; the reference itself cannot be built in this
+image) on the host cores with one process per core over independent frame ranges.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--features", type=int, default=2040)
+    ap.add_argument("--hyp", type=int, default=50)
+    ap.add_argument("--unique", type=int, default=64,
+                    help="distinct rendered frames; the sequence drives back and forth over them (every frame has "
+                         "its own HBM copy, so the working set is the full --frames)")
+    ap.add_argument("--cpu-pairs", type=int, default=96, help="frame pairs in the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def pingpong(n_frames, n_unique):
+    """frame t of the long sequence -> index into the rendered frames: 0,1,..,U-1,U-2,..,0,1,.."""
+    if n_unique <= 1:
+        return np.zeros(n_frames, np.int64)
+    period = 2 * (n_unique - 1)
+    t = np.arange(n_frames) % period
+    return np.where(t < n_unique, t, period - t)
+
+
+def build_sequence(args, seed, workers):
+    from libviso_b200 import synth
+    n_unique = min(args.unique, args.frames)
+    frames, _ = synth.make_sequence(n_unique, seed=seed, n_features=args.features, workers=workers)
+    order = pingpong(args.frames, n_unique)
+    return frames, order
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=10)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_oracle_pairs(frames, order, t0, n_pairs, H, seeds):
+    """run the CPU oracle over frames [t0, t0+n_pairs] of the long sequence; returns (seconds, records)"""
+    from oracle import oracle
+    from libviso_b200 import synth
+    P1, P2 = synth.kitti_calib()
+    sub = [frames[order[t]] for t in range(t0, t0 + n_pairs + 1)]
+    param = oracle.param_default(ransac_iter=H)
+    sd = np.ascontiguousarray(seeds[t0:t0 + n_pairs + 1])
+    t = time.perf_counter()
+    out = oracle.sequence(sub, P1, P2, param, sd)
+    return time.perf_counter() - t, out["records"]
+
+
+def make_seeds(n_frames, H, seed):
+    return np.random.default_rng(424242 + seed).integers(0, 2 ** 32, size=(n_frames, H, 3), dtype=np.uint32)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port) on the host cores"""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    frames, order = build_sequence(args, 1000, min(cores, 16))
+    seeds = make_seeds(args.frames, args.hyp, 1000)
+    pairs_per_proc = 6
+    jobs_per_step = cores
+    global _REF_STATE
+    _REF_STATE = (frames, order, seeds, args.hyp)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        def step(i):
+            starts = [((i * jobs_per_step + j) * pairs_per_proc) % max(args.frames - pairs_per_proc - 1, 1) for j in range(jobs_per_step)]
+            t = time.perf_counter()
+            pool.map(_ref_step, [(s, pairs_per_proc) for s in starts])
+            return time.perf_counter() - t
+        for i in range(args.warmup):
+            step(i)
+        times = [step(args.warmup + i) for i in range(args.steps)]
+    total = sum(times)
+    n_pairs = args.steps * jobs_per_step * pairs_per_proc
+    value = n_pairs / total
+    sample = (f"{jobs_per_step} processes x {pairs_per_proc} frame pairs per step, independent frame ranges of the same "
+              f"{args.frames}-frame sequence")
+    line = {
+        "impl": "reference", "metric": "frame-pairs/s (match+RANSAC pose) at 1241x376", "value": value,
+        "unit": "frame-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16 SAD / f64 pose", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+_REF_STATE = None
+
+
+def _ref_step(job):
+    t0, n_pairs = job
+    frames, order, seeds, H = _REF_STATE
+    return cpu_oracle_pairs(frames, order, t0, n_pairs, H, seeds)[0]
+
+
+def workload_config(args):
+    return {"workload": f"synthetic {args.frames}-frame KITTI-shaped stereo sequence per GPU (BASELINE configs[1]): "
+                        f"1241x376, ~{args.features} Harris features/image, 121-element Sobel descriptors, stereo + "
+                        f"2x temporal SAD matching, circle closure, triangulation, RANSAC({args.hyp}) + Gauss-Newton",
+            "frames": args.frames, "features": args.features, "ransac_iter": args.hyp,
+            "unique_rendered_frames": min(args.unique, args.frames),
+            "l2": "inputs larger than L2 (every frame has its own HBM copy: ~3 GB per sequence vs 126 MB L2)",
+            "parallelism": f"{args.gpus} independent sequence(s), one per GPU, NCCL gather of 64-byte records"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from libviso_b200 import api, build, synth
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libviso_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cores = os.cpu_count() or 1
+    frames, order = build_sequence(args, 1000 + rank, max(1, min(16, cores // world)))
+    F, H = args.frames, args.hyp
+    seeds = make_seeds(F, H, 1000 + rank)
+    P1, P2 = synth.kitti_calib()
+    cap = max(max(len(f["kpL"]), len(f["kpR"])) for f in frames)
+
+    ctx = api.Context(local_rank)
+    ctx.set_image_extent(synth.W, synth.H)
+    seq = ctx.sequence(F, cap, 121, H)
+    seq.set_calib(P1, P2)
+    param = api.param_default(ransac_iter=H)
+
+    # pinned host copies of the unique frames (the e2e path uploads from these every step)
+    pinned = []
+    for f in frames:
+        p = {}
+        for k in ("kpL", "kpR", "dL", "dR"):
+            tns = torch.from_numpy(np.ascontiguousarray(f[k], dtype=np.float32)).pin_memory()
+            p[k] = tns
+        p["nL"], p["nR"] = len(f["kpL"]), len(f["kpR"])
+        pinned.append(p)
+    seeds_pin = torch.from_numpy(seeds.view(np.int32)).pin_memory()
+    rec_pin = torch.zeros(F * 16, dtype=torch.int32).pin_memory()
+
+    def upload_all():
+        for t in range(F):
+            p = pinned[order[t]]
+            seq.upload_frame_raw(t, p["kpL"].data_ptr(), p["nL"], p["kpR"].data_ptr(), p["nR"],
+                                 p["dL"].data_ptr(), p["dR"].data_ptr())
+
+    h2d = sum((pinned[i]["nL"] + pinned[i]["nR"]) * (8 + 121 * 4) for i in order) + seeds.nbytes
+    d2h = F * 64
+    n_pairs = F - 1
+
+    # ---- device-resident throughput ----
+    upload_all()
+    seq.set_seeds(seeds, H)
+    ctx.sync()
+    for _ in range(max(args.warmup, 3)):
+        seq.run(param)
+    ctx.sync()
+    l0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    match_ms = []
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        seq.run(param)
+        match_ms.append(seq.match_ms())
+    dev_ms = ctx.timer_end()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    rec = seq.download()
+    match_bytes, sad_pairs, sad_eval = seq.stats()
+
+    # ---- end to end through the C-ABI with host buffers ----
+    e2e_ms = None
+    if not args.no_e2e:
+        def e2e_step():
+            upload_all()
+            ctx._ck(api.lib().viso_seq_set_seeds(seq.h, api._p(seeds_pin.data_ptr()), H))
+            seq.run(param)
+            seq.download_raw(rec_pin.data_ptr())
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ctx.timer_begin()
+        for _ in range(args.steps):
+            e2e_step()
+        e2e_ms = ctx.timer_end()
+        e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
+        e2e_ms = max(e2e_ms, e2e_wall_ms)  # the download synchronises every step; report the slower clock
+        barrier()
+        rec_e2e = np.frombuffer(rec_pin.numpy().tobytes(), dtype=api.RECORD_DTYPE)
+        assert rec_e2e.tobytes() == rec.tobytes(), "e2e records differ from the resident run"
+
+    # ---- max over ranks, gather records (the only collective: 64 B per frame pair) ----
+    tms = torch.tensor([dev_ms, e2e_ms or 0.0, float(np.mean(match_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        mine = torch.from_numpy(rec.view(np.int32).reshape(-1).copy()).cuda()
+        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, gathered, dst=0)
+        if rank == 0:
+            all_rec = [g.cpu().numpy().view(api.RECORD_DTYPE) for g in gathered]
+    else:
+        all_rec = [rec]
+    dev_ms, e2e_ms_g, mm = [float(v) for v in tms.cpu()]
+
+    if rank == 0:
+        n_poses = [len(api.chain_poses(r)) for r in all_rec]
+        value = world * n_pairs * args.steps / (dev_ms * 1e-3)
+        peak, peak_src = hbm_peak()
+        achieved = match_bytes / (mm * 1e-3) / 1e9
+        line = {
+            "metric": "frame-pairs/s (match+RANSAC pose) at 1241x376", "value": value, "unit": "frame-pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16 SAD / f64 pose",
+            "data": "synthetic", "config": workload_config(args),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "sad_match_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(match_bytes), "kernel_ms": mm,
+                         "sad_pairs_per_launch": int(sad_pairs), "sad_evaluated_per_launch": int(sad_eval),
+                         "kernel_share_of_step": mm / (dev_ms / args.steps)},
+            "poses": {"chained_per_sequence": n_poses, "ok_frame_pairs": int(sum(int(r["ok"].sum()) for r in all_rec))},
+        }
+        if e2e_ms is not None:
+            line["e2e"] = {"value": world * n_pairs * args.steps / (e2e_ms_g * 1e-3), "unit": "frame-pairs/s",
+                           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                           "ms_per_step": e2e_ms_g / args.steps}
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle
+            oracle.build()
+            npairs = min(args.cpu_pairs, n_pairs)
+            secs, rec_o = cpu_oracle_pairs(frames, order, 0, npairs, H, seeds)
+            same = all(np.array_equal(rec[k][:npairs + 1], rec_o[k]) for k in ("ok", "n_inliers", "n_circ", "best_hyp"))
+            line["cpu_baseline"] = {"value": npairs / secs, "unit": "frame-pairs/s", "cores": 1, "kind": "port",
+                                    "sample": f"first {npairs} frame pairs of the same sequence, CPU oracle "
+                                              f"(g++ -O2), {secs:.1f} s", "records_match_gpu": bool(same)}
+        print(json.dumps(line), flush=True)
+    seq.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

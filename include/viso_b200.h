@@ -173,9 +173,10 @@ int viso_seq_run_resident(viso_seq* seq, const viso_param* param);
 int viso_seq_download(viso_seq* seq, viso_record* records);
 /* rank-0 bookkeeping of viso.cpp:1189-1190,1313-1321: poses[0] = I, one 4x4 appended per ok record. returns count */
 int viso_chain_poses(const viso_record* records, int n_frames, double* poses /* (n_frames) x 16 */);
-/* algorithmic HBM bytes of the sad_match launch of one viso_seq_run (SURVEY 8d formula, int16 layout) and the
- * number of SAD candidate pairs it evaluated (valid after viso_seq_download) */
-int viso_seq_stats(viso_seq* seq, int64_t* match_bytes, int64_t* sad_pairs);
+/* algorithmic HBM bytes of the sad_match launch of one viso_seq_run (SURVEY 8d formula, int16 layout); the number of
+ * candidate pairs that reach the SAD in the reference (the survey's P); and the number of exact SADs the kernel
+ * actually evaluated after lower-bound pruning.  Any pointer may be NULL. */
+int viso_seq_stats(viso_seq* seq, int64_t* match_bytes, int64_t* sad_pairs, int64_t* sad_evaluated);
 /* elapsed ms of the sad_match kernel in the last run (CUDA events on the context stream) */
 int viso_seq_match_ms(viso_seq* seq, float* ms);
 /* parity-test getters (host copies).  which: 0 = stereo (frame t), 1 = temporal left (t vs t-1), 2 = temporal right */

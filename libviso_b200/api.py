@@ -344,9 +344,9 @@ class Sequence:
         self.ctx._ck(lib().viso_seq_download(self.h, _p(ptr)))
 
     def stats(self):
-        mb = C.c_int64(0); sp = C.c_int64(0)
-        self.ctx._ck(lib().viso_seq_stats(self.h, C.byref(mb), C.byref(sp)))
-        return mb.value, sp.value
+        mb = C.c_int64(0); sp = C.c_int64(0); se = C.c_int64(0)
+        self.ctx._ck(lib().viso_seq_stats(self.h, C.byref(mb), C.byref(sp), C.byref(se)))
+        return mb.value, sp.value, se.value
 
     def match_ms(self):
         ms = C.c_float(0)

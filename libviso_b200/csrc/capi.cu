@@ -294,10 +294,12 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
     const int ncell = ctx->ncell();
 
     struct Bufs {
-        float2 *xy1, *xy2, *sxy1, *sxy2;
+        float2 *xy1, *xy2;
+        uint4 *srec1, *srec2, *sps1, *sps2;
+        unsigned *ps1, *ps2, *rs1, *rs2;
         float *df1, *df2;
         uint16_t *du1, *du2;
-        int *sidx1, *sidx2, *cell1, *cell2, *counts, *err, *matches, *mcount;
+        int *cell1, *cell2, *counts, *err, *matches, *mcount;
         int4* out;
         unsigned long long* pairs;
         PackJob* pack;
@@ -307,10 +309,12 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
     } b;
     auto carve = [&](Carver& c) {
         b.xy1 = c.take<float2>(n1); b.xy2 = c.take<float2>(n2);
-        b.sxy1 = c.take<float2>(n1); b.sxy2 = c.take<float2>(n2);
+        b.srec1 = c.take<uint4>(n1); b.srec2 = c.take<uint4>(n2);
+        b.sps1 = c.take<uint4>((size_t)n1 * 2); b.sps2 = c.take<uint4>((size_t)n2 * 2);
+        b.ps1 = c.take<unsigned>((size_t)n1 * 8); b.ps2 = c.take<unsigned>((size_t)n2 * 8);
+        b.rs1 = c.take<unsigned>(n1); b.rs2 = c.take<unsigned>(n2);
         b.df1 = c.take<float>((size_t)n1 * dlen); b.df2 = c.take<float>((size_t)n2 * dlen);
         b.du1 = c.take<uint16_t>((size_t)n1 * VISO_DESC_U16); b.du2 = c.take<uint16_t>((size_t)n2 * VISO_DESC_U16);
-        b.sidx1 = c.take<int>(n1); b.sidx2 = c.take<int>(n2);
         b.cell1 = c.take<int>(ncell + 1); b.cell2 = c.take<int>(ncell + 1);
         b.counts = c.take<int>(4); b.err = c.take<int>(1);
         b.matches = c.take<int>((size_t)n1 * 3); b.mcount = c.take<int>(1);
@@ -335,11 +339,12 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
         CK(cudaMemcpyAsync(b.xy2, kp2, (size_t)n2 * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(b.df2, d2, (size_t)n2 * dlen * 4, cudaMemcpyHostToDevice, s));
     }
-    PackJob pj[2] = {{b.df1, b.counts, b.du1}, {b.df2, b.counts + 1, b.du2}};
-    GridJob gj[2] = {{b.xy1, b.counts, b.sxy1, b.sidx1, b.cell1}, {b.xy2, b.counts + 1, b.sxy2, b.sidx2, b.cell2}};
+    PackJob pj[2] = {{b.df1, b.counts, b.du1, b.ps1, b.rs1}, {b.df2, b.counts + 1, b.du2, b.ps2, b.rs2}};
+    GridJob gj[2] = {{b.xy1, b.counts, b.ps1, b.rs1, b.srec1, b.sps1, b.cell1},
+                     {b.xy2, b.counts + 1, b.ps2, b.rs2, b.srec2, b.sps2, b.cell2}};
     MatchJob mj;
-    mj.q = SetView{b.xy1, b.counts, b.du1, b.sxy1, b.sidx1, b.cell1};
-    mj.t = SetView{b.xy2, b.counts + 1, b.du2, b.sxy2, b.sidx2, b.cell2};
+    mj.q = SetView{b.xy1, b.counts, b.du1, b.srec1, b.sps1, b.cell1};
+    mj.t = SetView{b.xy2, b.counts + 1, b.du2, b.srec2, b.sps2, b.cell2};
     mj.out = b.out; mj.mode = 0; mj.pad = 0;
     SortJob sj;
     sj.dense = b.out; sj.n = b.counts; sj.kp1 = b.xy1; sj.kp2 = b.xy2; sj.matches = b.matches; sj.count = b.mcount;
@@ -361,7 +366,7 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
     int flags = 0, mcount = 0;
     if (sorted) {
         ParamDev pd{};
-        CK(viso_launch_sort(b.sort, 1, pd, s));
+        CK(viso_launch_sort(b.sort, 1, n1, pd, s));
         ctx->launches += 1;
         host_m.resize((size_t)n1 * 3);
         CK(cudaMemcpyAsync(host_m.data(), b.matches, (size_t)n1 * 12, cudaMemcpyDeviceToHost, s));
@@ -848,10 +853,12 @@ struct viso_seq {
     viso_ctx* ctx = nullptr;
     int F = 0, cap = 0, dlen = 0, maxH = 0, ncell = 0;
     GridCfg grid{};
-    float2 *kpL = nullptr, *kpR = nullptr, *sxyL = nullptr, *sxyR = nullptr;
+    float2 *kpL = nullptr, *kpR = nullptr;
+    uint4 *srecL = nullptr, *srecR = nullptr, *spsL = nullptr, *spsR = nullptr;
+    unsigned *psL = nullptr, *psR = nullptr, *rsL = nullptr, *rsR = nullptr;
     float *dLf = nullptr, *dRf = nullptr;
     uint16_t *dLu = nullptr, *dRu = nullptr;
-    int *nL = nullptr, *nR = nullptr, *sidxL = nullptr, *sidxR = nullptr, *cellL = nullptr, *cellR = nullptr;
+    int *nL = nullptr, *nR = nullptr, *cellL = nullptr, *cellR = nullptr;
     int4 *dense_lr = nullptr, *dense_11 = nullptr, *dense_22 = nullptr;
     int *lr = nullptr, *lr_count = nullptr, *pos = nullptr;
     double *x = nullptr, *X = nullptr, *x_c = nullptr, *Xp_c = nullptr;
@@ -922,10 +929,11 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
             return e__ == cudaErrorMemoryAllocation ? VISO_ERR_NOMEM : VISO_ERR_CUDA;    \
         }                                                                                \
     } while (0)
-    SA(kpL, F * cap); SA(kpR, F * cap); SA(sxyL, F * cap); SA(sxyR, F * cap);
+    SA(kpL, F * cap); SA(kpR, F * cap); SA(srecL, F * cap); SA(srecR, F * cap);
+    SA(spsL, F * cap * 2); SA(spsR, F * cap * 2); SA(psL, F * cap * 8); SA(psR, F * cap * 8); SA(rsL, F * cap); SA(rsR, F * cap);
     SA(dLf, F * cap * desc_len); SA(dRf, F * cap * desc_len);
     SA(dLu, F * cap * VISO_DESC_U16); SA(dRu, F * cap * VISO_DESC_U16);
-    SA(nL, F); SA(nR, F); SA(sidxL, F * cap); SA(sidxR, F * cap); SA(cellL, F * nc); SA(cellR, F * nc);
+    SA(nL, F); SA(nR, F); SA(cellL, F * nc); SA(cellR, F * nc);
     SA(dense_lr, F * cap); SA(dense_11, F * cap); SA(dense_22, F * cap);
     SA(lr, F * cap * 3); SA(lr_count, F); SA(pos, F * cap);
     SA(x, F * cap * 4); SA(X, F * cap * 3); SA(x_c, F * cap * 4); SA(Xp_c, F * cap * 3);
@@ -934,7 +942,7 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     SA(hyp_ok, F * H); SA(hyp_count, F * H); SA(inliers, F * cap); SA(active, F * cap);
     SA(rec, F); SA(seeds, F * H * 3);
     SA(pack_jobs, 2 * F); SA(grid_jobs, 2 * F); SA(match_jobs, 3 * F); SA(sort_jobs, F); SA(circ_jobs, F); SA(probs, F);
-    SA(pairs, 1); SA(err, 1);
+    SA(pairs, 2); SA(err, 1);
 #undef SA
     s->h_nL.assign(F, 0);
     s->h_nR.assign(F, 0);
@@ -948,7 +956,7 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     if ((e = cudaMemsetAsync(s->lr_count, 0, F * 4, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
     if ((e = cudaMemsetAsync(s->n_circ, 0, F * 4, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
     if ((e = cudaMemsetAsync(s->rec, 0, F * sizeof(viso_record_dev), st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
-    if ((e = cudaMemsetAsync(s->pairs, 0, 8, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
+    if ((e = cudaMemsetAsync(s->pairs, 0, 16, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
     if ((e = cudaMemsetAsync(s->err, 0, 4, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
 
     /* job tables: all pointers are fixed for the life of the object */
@@ -959,18 +967,22 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     std::vector<CircleJob> cj(F);
     s->h_probs.resize(F);
     auto viewL = [&](size_t t) {
-        return SetView{s->kpL + t * cap, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->sxyL + t * cap, s->sidxL + t * cap,
-                       s->cellL + t * nc};
+        return SetView{s->kpL + t * cap, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->srecL + t * cap,
+                       s->spsL + t * cap * 2, s->cellL + t * nc};
     };
     auto viewR = [&](size_t t) {
-        return SetView{s->kpR + t * cap, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->sxyR + t * cap, s->sidxR + t * cap,
-                       s->cellR + t * nc};
+        return SetView{s->kpR + t * cap, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->srecR + t * cap,
+                       s->spsR + t * cap * 2, s->cellR + t * nc};
     };
     for (size_t t = 0; t < F; ++t) {
-        pj[2 * t] = PackJob{s->dLf + t * cap * desc_len, s->nL + t, s->dLu + t * cap * VISO_DESC_U16};
-        pj[2 * t + 1] = PackJob{s->dRf + t * cap * desc_len, s->nR + t, s->dRu + t * cap * VISO_DESC_U16};
-        gj[2 * t] = GridJob{s->kpL + t * cap, s->nL + t, s->sxyL + t * cap, s->sidxL + t * cap, s->cellL + t * nc};
-        gj[2 * t + 1] = GridJob{s->kpR + t * cap, s->nR + t, s->sxyR + t * cap, s->sidxR + t * cap, s->cellR + t * nc};
+        pj[2 * t] = PackJob{s->dLf + t * cap * desc_len, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->psL + t * cap * 8,
+                            s->rsL + t * cap};
+        pj[2 * t + 1] = PackJob{s->dRf + t * cap * desc_len, s->nR + t, s->dRu + t * cap * VISO_DESC_U16,
+                                s->psR + t * cap * 8, s->rsR + t * cap};
+        gj[2 * t] = GridJob{s->kpL + t * cap, s->nL + t, s->psL + t * cap * 8, s->rsL + t * cap, s->srecL + t * cap,
+                            s->spsL + t * cap * 2, s->cellL + t * nc};
+        gj[2 * t + 1] = GridJob{s->kpR + t * cap, s->nR + t, s->psR + t * cap * 8, s->rsR + t * cap, s->srecR + t * cap,
+                                s->spsR + t * cap * 2, s->cellR + t * nc};
         MatchJob m;
         m.pad = 0;
         m.q = viewL(t); m.t = viewR(t); m.out = s->dense_lr + t * cap; m.mode = 0; /* stereo, viso.cpp:1240 */
@@ -1088,7 +1100,7 @@ int viso_seq_run_resident(viso_seq* s, const viso_param* param)
     const int F = s->F;
     CK(cudaMemcpyAsync(s->nL, s->h_nL.data(), (size_t)F * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->nR, s->h_nR.data(), (size_t)F * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(s->pairs, 0, 8, st));
+    CK(cudaMemsetAsync(s->pairs, 0, 16, st));
     CK(cudaMemsetAsync(s->err, 0, 4, st));
     int max_n = 0, max_nL = 0;
     for (int t = 0; t < F; ++t) {
@@ -1110,7 +1122,7 @@ int viso_seq_run_resident(viso_seq* s, const viso_param* param)
     CK(cudaEventRecord(s->ev0, st));
     CK(viso_launch_match(s->match_jobs, 3 * F - 2, max_n, mp, s->grid, s->pairs, st));
     CK(cudaEventRecord(s->ev1, st));
-    CK(viso_launch_sort(s->sort_jobs, F, pd, st));
+    CK(viso_launch_sort(s->sort_jobs, F, max_nL, pd, st));
     ctx->launches += (max_n > 0 ? 3 : 1) + 1;
     if (F > 1) {
         CK(viso_launch_circle(s->circ_jobs + 1, F - 1, st));
@@ -1151,7 +1163,7 @@ int viso_seq_download(viso_seq* s, viso_record* records)
     return status_from_flags(ctx, flags);
 }
 
-int viso_seq_stats(viso_seq* s, int64_t* match_bytes, int64_t* sad_pairs)
+int viso_seq_stats(viso_seq* s, int64_t* match_bytes, int64_t* sad_pairs, int64_t* sad_evaluated)
 {
     if (!s) return VISO_ERR_ARG;
     viso_ctx* ctx = s->ctx;
@@ -1166,11 +1178,12 @@ int viso_seq_stats(viso_seq* s, int64_t* match_bytes, int64_t* sad_pairs)
         }
         *match_bytes = b;
     }
-    if (sad_pairs) {
-        unsigned long long p = 0;
-        CK(cudaMemcpyAsync(&p, s->pairs, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sad_pairs || sad_evaluated) {
+        unsigned long long p[2] = {0, 0};
+        CK(cudaMemcpyAsync(p, s->pairs, 16, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        *sad_pairs = (int64_t)p;
+        if (sad_pairs) *sad_pairs = (int64_t)p[0];
+        if (sad_evaluated) *sad_evaluated = (int64_t)p[1];
     }
     return VISO_OK;
 }

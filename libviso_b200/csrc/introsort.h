@@ -23,15 +23,17 @@
 namespace viso_sort {
 
 struct M3 { int32_t a, b, d; };
+/* (dist, payload): sorts exactly like M3 because the algorithm only looks at d */
+struct KV { int32_t d, pos; };
 
-VISO_HD bool less(const M3& x, const M3& y) { return x.d < y.d; }
-VISO_HD void swp(M3* p, int i, int j) { M3 t = p[i]; p[i] = p[j]; p[j] = t; }
+template <class T> VISO_HD bool less(const T& x, const T& y) { return x.d < y.d; }
+template <class T> VISO_HD void swp(T* p, int i, int j) { T t = p[i]; p[i] = p[j]; p[j] = t; }
 
 /* std::__lg */
 VISO_HD int lg(int n) { int k = 0; while (n > 1) { n >>= 1; ++k; } return k; }
 
 /* std::__push_heap */
-VISO_HD void push_heap_(M3* first, int hole, int top, M3 value)
+template <class T> VISO_HD void push_heap_(T* first, int hole, int top, T value)
 {
     int parent = (hole - 1) / 2;
     while (hole > top && less(first[parent], value)) {
@@ -43,7 +45,7 @@ VISO_HD void push_heap_(M3* first, int hole, int top, M3 value)
 }
 
 /* std::__adjust_heap */
-VISO_HD void adjust_heap_(M3* first, int hole, int len, M3 value)
+template <class T> VISO_HD void adjust_heap_(T* first, int hole, int len, T value)
 {
     const int top = hole;
     int child = hole;
@@ -62,12 +64,12 @@ VISO_HD void adjust_heap_(M3* first, int hole, int len, M3 value)
 }
 
 /* std::__partial_sort(first, last, last) == __heap_select (make_heap only, middle==last) + __sort_heap */
-VISO_HD void heap_sort_(M3* first, int len)
+template <class T> VISO_HD void heap_sort_(T* first, int len)
 {
     if (len >= 2) {
         int parent = (len - 2) / 2;
         while (true) {
-            M3 v = first[parent];
+            T v = first[parent];
             adjust_heap_(first, parent, len, v);
             if (parent == 0) break;
             parent--;
@@ -76,14 +78,14 @@ VISO_HD void heap_sort_(M3* first, int len)
     int last = len;
     while (last > 1) {
         --last;
-        M3 v = first[last];          /* __pop_heap(first, last, last) */
+        T v = first[last];          /* __pop_heap(first, last, last) */
         first[last] = first[0];
         adjust_heap_(first, 0, last, v);
     }
 }
 
 /* std::__move_median_to_first(result, a, b, c) */
-VISO_HD void median_to_first_(M3* p, int result, int a, int b, int c)
+template <class T> VISO_HD void median_to_first_(T* p, int result, int a, int b, int c)
 {
     if (less(p[a], p[b])) {
         if (less(p[b], p[c])) swp(p, result, b);
@@ -95,7 +97,7 @@ VISO_HD void median_to_first_(M3* p, int result, int a, int b, int c)
 }
 
 /* std::__unguarded_partition(first, last, pivot) */
-VISO_HD int unguarded_partition_(M3* p, int first, int last, int pivot)
+template <class T> VISO_HD int unguarded_partition_(T* p, int first, int last, int pivot)
 {
     while (true) {
         while (less(p[first], p[pivot])) ++first;
@@ -108,9 +110,9 @@ VISO_HD int unguarded_partition_(M3* p, int first, int last, int pivot)
 }
 
 /* std::__unguarded_linear_insert */
-VISO_HD void unguarded_linear_insert_(M3* p, int last)
+template <class T> VISO_HD void unguarded_linear_insert_(T* p, int last)
 {
-    M3 val = p[last];
+    T val = p[last];
     int next = last - 1;
     while (less(val, p[next])) {
         p[last] = p[next];
@@ -121,12 +123,12 @@ VISO_HD void unguarded_linear_insert_(M3* p, int last)
 }
 
 /* std::__insertion_sort */
-VISO_HD void insertion_sort_(M3* p, int first, int last)
+template <class T> VISO_HD void insertion_sort_(T* p, int first, int last)
 {
     if (first == last) return;
     for (int i = first + 1; i != last; ++i) {
         if (less(p[i], p[first])) {
-            M3 val = p[i];
+            T val = p[i];
             for (int k = i; k > first; --k) p[k] = p[k - 1]; /* std::move_backward(first, i, i+1) */
             p[first] = val;
         } else
@@ -135,7 +137,7 @@ VISO_HD void insertion_sort_(M3* p, int first, int last)
 }
 
 /* std::sort(p, p+n, less) */
-VISO_HD void sort(M3* p, int n)
+template <class T> VISO_HD void sort(T* p, int n)
 {
     const int S_threshold = 16;
     if (n <= 0) return;

@@ -67,6 +67,12 @@ __device__ __forceinline__ int block_compact_slot(bool flag, int& base_io, int* 
 
 /* ------------------------------------------------------------------------------------------------ pack */
 
+/*
+ * f32 cv::Mat descriptor rows (viso.cpp:999-1002) -> biased u16 rows (v + 1024, pad elements 0), plus per row
+ *   psum[16]  u16 sums of the 16 groups of 8 consecutive elements (one uint4 of the packed row each)
+ *   rsum      u32 sum of the whole packed row
+ * One warp per row, lane l owns elements 4l..4l+3.  Also the domain check (integer valued, |v| <= 1023).
+ */
 __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restrict__ jobs, int dlen, int* err)
 {
     const PackJob job = jobs[blockIdx.y];
@@ -90,12 +96,16 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
             u[e] = v;
             sum += v;
         }
-        sum = warp_sum_u(sum);
         uint2 w;
         w.x = u[0] | (u[1] << 16);
         w.y = u[2] | (u[3] << 16);
-        if (lane == 31) w.y = sum; /* elements 126,127 carry the row sum */
         reinterpret_cast<uint2*>(job.out + (size_t)row * VISO_DESC_U16)[lane] = w;
+        /* group sums: group p = lanes 2p, 2p+1 */
+        unsigned g = sum + __shfl_xor_sync(FULL, sum, 1);
+        unsigned g2 = __shfl_down_sync(FULL, g, 2);       /* lane 4j: group 2j+1 */
+        if ((lane & 3) == 0) job.psum[(size_t)row * 8 + (lane >> 2)] = g | (g2 << 16);
+        const unsigned tot = warp_sum_u(sum);
+        if (lane == 0) job.rsum[row] = tot;
         if (bad) atomicOr(err, 1);
     }
 }
@@ -108,6 +118,10 @@ __device__ __forceinline__ int cell_coord(float v, int g)
     return min(max(c, 0), g - 1);
 }
 
+/*
+ * Counting sort of one keypoint set into 16-px cells (one CTA per set).  Emits, in cell order, the candidate
+ * records the matcher streams: srec = (x, y, original index, row sum) and the 32-byte group-sum vector.
+ */
 __global__ void __launch_bounds__(512) grid_build_kernel(const GridJob* __restrict__ jobs, GridCfg g)
 {
     extern __shared__ int sm[];
@@ -141,11 +155,13 @@ __global__ void __launch_bounds__(512) grid_build_kernel(const GridJob* __restri
         if (c < ncell) cursor[c] = v;
     }
     __syncthreads();
+    const uint4* ps = reinterpret_cast<const uint4*>(job.psum);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         float2 p = job.xy[i];
         int pos = atomicAdd(&cursor[cell_coord(p.y, g.gy) * g.gx + cell_coord(p.x, g.gx)], 1);
-        job.sxy[pos] = p;
-        job.sidx[pos] = i;
+        job.srec[pos] = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), (unsigned)i, job.rsum[i]);
+        job.spsum[2 * pos] = ps[2 * i];
+        job.spsum[2 * pos + 1] = ps[2 * i + 1];
     }
 }
 
@@ -185,73 +201,76 @@ struct WarpScratch {
     int tieI[VISO_TIE_CAP];
 };
 
-/* Enumerate, warp-cooperatively and flattened over grid rows, every target point in the cells overlapping the
- * L1 diamond of radius r around (qx,qy).  f(in, dist, idx) is called by all 32 lanes for each chunk of 32. */
-template <class Fn>
-__device__ __forceinline__ void enumerate_candidates(const SetView& t, GridCfg g, float qx, float qy, float r,
-                                                     WarpScratch& ws, int lane, Fn&& f)
+struct QueryGeom {
+    float qx, qy, r, slack;
+    int cy0, cy1;
+};
+
+__device__ __forceinline__ QueryGeom make_geom(GridCfg g, float qx, float qy, float r)
 {
-    const float slack = 1.0f + 4e-6f * (fabsf(qx) + fabsf(qy) + r);
-    const int cy0 = cell_coord(qy - r - slack, g.gy), cy1 = cell_coord(qy + r + slack, g.gy);
-    for (int rg = cy0; rg <= cy1; rg += 32) {
-        const int cy = rg + lane;
-        int s0 = 0, len = 0;
-        if (cy <= cy1) {
-            const float lo = (cy == 0) ? -CUDART_INF_F : (float)(cy * VISO_GRID_CS);
-            const float hi = (cy == g.gy - 1) ? CUDART_INF_F : (float)((cy + 1) * VISO_GRID_CS);
-            const float dymin = fmaxf(0.f, fmaxf(lo - qy, qy - hi));
-            const float rem = r - dymin + slack;
-            if (rem >= 0.f) {
-                const int cx0 = cell_coord(qx - rem, g.gx), cx1 = cell_coord(qx + rem, g.gx);
-                s0 = t.cell_start[cy * g.gx + cx0];
-                len = t.cell_start[cy * g.gx + cx1 + 1] - s0;
-            }
+    QueryGeom q;
+    q.qx = qx; q.qy = qy; q.r = r;
+    q.slack = 1.0f + 4e-6f * (fabsf(qx) + fabsf(qy) + r);
+    q.cy0 = cell_coord(qy - r - q.slack, g.gy);
+    q.cy1 = cell_coord(qy + r + q.slack, g.gy);
+    return q;
+}
+
+/* Spans of the (up to 32) grid rows rg..rg+31 that overlap the L1 diamond: lane l owns row rg+l.  Leaves the
+ * flattened prefix table in ws and returns the number of points in those spans (same value in all lanes). */
+__device__ __forceinline__ int setup_rows(const SetView& t, GridCfg g, const QueryGeom& q, int rg, WarpScratch& ws, int lane)
+{
+    const int cy = rg + lane;
+    int s0 = 0, len = 0;
+    if (cy <= q.cy1) {
+        const float lo = (cy == 0) ? -CUDART_INF_F : (float)(cy * VISO_GRID_CS);
+        const float hi = (cy == g.gy - 1) ? CUDART_INF_F : (float)((cy + 1) * VISO_GRID_CS);
+        const float dymin = fmaxf(0.f, fmaxf(lo - q.qy, q.qy - hi));
+        const float rem = q.r - dymin + q.slack;
+        if (rem >= 0.f) {
+            const int cx0 = cell_coord(q.qx - rem, g.gx), cx1 = cell_coord(q.qx + rem, g.gx);
+            s0 = t.cell_start[cy * g.gx + cx0];
+            len = t.cell_start[cy * g.gx + cx1 + 1] - s0;
         }
-        const int incl = warp_incl_scan(len, lane);
-        __syncwarp();
-        ws.rowS0[lane] = s0;
-        ws.rowPre[lane] = incl - len;
-        if (lane == 31) ws.rowPre[32] = incl;
-        __syncwarp();
-        const int total = __shfl_sync(FULL, incl, 31);
-        int row = 0;
-        for (int base = 0; base < total; base += 32) {
-            const int fl = base + lane;
-            const bool in = fl < total;
-            float dist = CUDART_INF_F;
-            int idx = -1;
-            if (in) {
-                while (fl >= ws.rowPre[row + 1]) ++row;
-                const int p = ws.rowS0[row] + (fl - ws.rowPre[row]);
-                const float2 xy = t.sxy[p];
-                idx = t.sidx[p];
-                dist = l1_dist(qx, qy, xy.x, xy.y);
-            }
-            f(in, dist, idx);
+    }
+    const int incl = warp_incl_scan(len, lane);
+    __syncwarp();
+    ws.rowS0[lane] = s0;
+    ws.rowPre[lane] = incl - len;
+    if (lane == 31) ws.rowPre[32] = incl;
+    __syncwarp();
+    return __shfl_sync(FULL, incl, 31);
+}
+
+/* Visit the points of the spans prepared by setup_rows, 32 per step: f(in, dist, rec, pos) is called by all lanes;
+ * rec = (x, y, original index, row sum) and pos the cell-sorted position of this lane's point. */
+template <class Fn>
+__device__ __forceinline__ void visit_rows(const SetView& t, const QueryGeom& q, int total, WarpScratch& ws, int lane, Fn&& f)
+{
+    int row = 0;
+    for (int base = 0; base < total; base += 32) {
+        const int fl = base + lane;
+        const bool in = fl < total;
+        float dist = CUDART_INF_F;
+        uint4 rec = make_uint4(0, 0, 0xffffffffu, 0);
+        int p = 0;
+        if (in) {
+            while (fl >= ws.rowPre[row + 1]) ++row;
+            p = ws.rowS0[row] + (fl - ws.rowPre[row]);
+            rec = __ldg(t.srec + p);
+            dist = l1_dist(q.qx, q.qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
         }
+        f(in, dist, rec, p);
     }
 }
 
-/* upper bound on the number of points enumerate_candidates visits (sum of the span lengths): if it is <= K the
- * top-K truncation cannot bind and one enumeration pass suffices */
-__device__ __forceinline__ int enumerate_bound(const SetView& t, GridCfg g, float qx, float qy, float r, int lane)
+template <class Fn>
+__device__ __forceinline__ void visit_all(const SetView& t, GridCfg g, const QueryGeom& q, WarpScratch& ws, int lane, Fn&& f)
 {
-    const float slack = 1.0f + 4e-6f * (fabsf(qx) + fabsf(qy) + r);
-    const int cy0 = cell_coord(qy - r - slack, g.gy), cy1 = cell_coord(qy + r + slack, g.gy);
-    int tot = 0;
-    for (int cy = cy0 + lane; cy <= cy1; cy += 32) {
-        const float lo = (cy == 0) ? -CUDART_INF_F : (float)(cy * VISO_GRID_CS);
-        const float hi = (cy == g.gy - 1) ? CUDART_INF_F : (float)((cy + 1) * VISO_GRID_CS);
-        const float dymin = fmaxf(0.f, fmaxf(lo - qy, qy - hi));
-        const float rem = r - dymin + slack;
-        if (rem >= 0.f) {
-            const int cx0 = cell_coord(qx - rem, g.gx), cx1 = cell_coord(qx + rem, g.gx);
-            tot += t.cell_start[cy * g.gx + cx1 + 1] - t.cell_start[cy * g.gx + cx0];
-        }
+    for (int rg = q.cy0; rg <= q.cy1; rg += 32) {
+        const int total = setup_rows(t, g, q, rg, ws, lane);
+        visit_rows(t, q, total, ws, lane, f);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-    return tot;
 }
 
 __device__ __forceinline__ int dist_bin(float dist, float scale)
@@ -260,7 +279,7 @@ __device__ __forceinline__ int dist_bin(float dist, float scale)
 }
 
 /*
- * match_desc, viso.cpp:668-722.  One warp per query.
+ * match_desc, viso.cpp:668-722.  One warp per query; the candidates of a query are visited 32 at a time, one per lane.
  *
  * Reference semantics restated set-wise: with D0 = L1(query, target 0) if that is <= radius
  * (else +inf), the scanned candidates are the K smallest keys (L1, index) among
@@ -268,10 +287,17 @@ __device__ __forceinline__ int dist_bin(float dist, float scale)
  * (target 0 terminates the reference's scan, viso.cpp:693, and sorts first inside its distance group, so exactly
  * the strictly closer points are scanned).  Over that set: best = min SAD, ties to the LARGEST key (the last one
  * in scan order, viso.cpp:703), best_d2 = second smallest SAD with multiplicity.  Sampson-gated candidates
- * (viso.cpp:695-701) still occupy a top-K slot but are not compared.
+ * (viso.cpp:695-701) still occupy a top-K slot but are not compared.  All of it is order independent, which is
+ * what allows the exact pruning below.
  *
- * SAD on biased u16 rows: sum|a-b| = sum(a) + sum(b) - 2*sum(min(a,b)); VIMNMX.U16x2 + IADD, 16 lanes x uint4
- * per 256-byte row, two candidates per warp step.
+ * SAD on biased u16 rows: sum|a-b| = sum(a) + sum(b) - 2*sum(min(a,b))  (VIMNMX.U16x2 + IADD, REDUX.SUM across the
+ * warp, 8 bytes of the 256-byte row per lane).
+ *
+ * Exact pruning: with the 16 group sums A_p, B_p of a row pair,  LB = sum_p |A_p - B_p| <= SAD  (triangle
+ * inequality per group).  LB costs 32 bytes and ~20 instructions per candidate and is evaluated by every lane for
+ * its own candidate; a candidate whose LB exceeds the current second-best SAD can change neither best nor
+ * second-best and is skipped.  Survivors are evaluated smallest-LB first (CREDUX.MIN picks the lane), so the
+ * bounds tighten after the first two and most candidates never have their descriptor row read.
  */
 __global__ void __launch_bounds__(VISO_MATCH_WARPS * 32)
 sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, unsigned long long* sad_pairs)
@@ -280,20 +306,22 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     const MatchJob job = jobs[blockIdx.y];
     const MatchParamsDev& P = mp.p[job.mode];
     const int nq = *job.q.n, nt = *job.t.n;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane & 15;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch& ws = wscr[warp];
     const float r = P.radius;
     const int K = P.K;
     const float bscale = (float)VISO_HIST_BINS / (r + 1.0f);
-    unsigned long long pairs = 0;
+    unsigned pairs_ref = 0, pairs_eval = 0;
 
     const int q_end = min(nq, (int)(blockIdx.x + 1) * VISO_MATCH_QPC);
     for (int qi = blockIdx.x * VISO_MATCH_QPC + warp; qi < q_end; qi += VISO_MATCH_WARPS) {
-        const int q = job.q.sidx[qi]; /* spatially sorted processing order */
-        const float2 qxy = job.q.xy[q];
-        const float qx = qxy.x, qy = qxy.y;
-        uint4 qd = __ldg(reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + h);
-        const unsigned qsum = __shfl_sync(FULL, qd.w, 15);
+        /* spatially sorted processing order: neighbouring warps stream the same candidate records */
+        const uint4 qrec = __ldg(job.q.srec + qi);
+        const int q = (int)qrec.z;
+        const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
+        const unsigned qsum = qrec.w;
+        const uint2 qd = __ldg(reinterpret_cast<const uint2*>(job.q.desc + (size_t)q * VISO_DESC_U16) + lane);
+        const uint4 qa = __ldg(job.q.spsum + 2 * qi), qb = __ldg(job.q.spsum + 2 * qi + 1);
 
         int b1 = INT_MAX, b2 = INT_MAX, bidx = -1;
         float bdist = -1.f;
@@ -303,17 +331,26 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
             const float2 t0 = job.t.xy[0];
             const float d0 = l1_dist(qx, qy, t0.x, t0.y);
             const float D0 = (d0 <= r) ? d0 : CUDART_INF_F;
+            const QueryGeom geom = make_geom(g, qx, qy, r);
+            const bool one_group = geom.cy1 - geom.cy0 < 32;
+
+            /* upper bound on the in-radius count: the number of points in the visited spans */
+            int total0 = setup_rows(job.t, g, geom, geom.cy0, ws, lane);
+            int bound = total0;
+            if (!one_group)
+                for (int rg = geom.cy0 + 32; rg <= geom.cy1; rg += 32) bound += setup_rows(job.t, g, geom, rg, ws, lane);
+            bool rows_ready = one_group;
 
             /* top-K threshold: (Tbin, Td, Ti); candidates with bin < Tbin, or bin == Tbin and key <= (Td,Ti) */
             int Tbin = INT_MAX;
             float Td = CUDART_INF_F;
             int Ti = INT_MAX;
-            const int bound = enumerate_bound(job.t, g, qx, qy, r, lane);
             if (bound > K) {
+                rows_ready = false;
                 for (int b = lane; b < VISO_HIST_BINS; b += 32) ws.hist[b] = 0;
                 __syncwarp();
                 int cnt = 0;
-                enumerate_candidates(job.t, g, qx, qy, r, ws, lane, [&](bool in, float dist, int idx) {
+                visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec, int) {
                     const bool inL = in && dist <= r && dist < D0;
                     if (inL) atomicAdd(&ws.hist[dist_bin(dist, bscale)], 1u);
                     cnt += __popc(__ballot_sync(FULL, inL));
@@ -345,13 +382,13 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                     if (m < nb) {
                         if (nb <= VISO_TIE_CAP) {
                             int fill = 0;
-                            enumerate_candidates(job.t, g, qx, qy, r, ws, lane, [&](bool in, float dist, int idx) {
+                            visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec, int) {
                                 const bool hitb = in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb;
                                 const unsigned bm = __ballot_sync(FULL, hitb);
                                 if (hitb) {
                                     const int o = fill + __popc(bm & ((1u << lane) - 1));
                                     ws.tieD[o] = dist;
-                                    ws.tieI[o] = idx;
+                                    ws.tieI[o] = (int)rec.z;
                                 }
                                 fill += __popc(bm);
                             });
@@ -373,7 +410,8 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                             float curD = -1.f; int curI = -1;
                             for (int it = 0; it < m; ++it) {
                                 float bestD = CUDART_INF_F; int bestI = INT_MAX;
-                                enumerate_candidates(job.t, g, qx, qy, r, ws, lane, [&](bool in, float dist, int idx) {
+                                visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec, int) {
+                                    const int idx = (int)rec.z;
                                     if (in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb &&
                                         key_greater(dist, idx, curD, curI) && key_greater(bestD, bestI, dist, idx)) {
                                         bestD = dist; bestI = idx;
@@ -393,56 +431,55 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 }
             }
 
-            /* final pass: Sampson gate + SAD, two candidates per step (one per half warp) */
-            enumerate_candidates(job.t, g, qx, qy, r, ws, lane, [&](bool in, float dist, int idx) {
+            /* final pass: membership, Sampson gate, lower bound, exact SAD of the survivors */
+            auto final_chunk = [&](bool in, float dist, uint4 rec, int pos) {
+                const int idx = (int)rec.z;
                 bool take = in && dist <= r && dist < D0;
                 if (take && Tbin != INT_MAX) {
                     const int bin = dist_bin(dist, bscale);
                     take = bin < Tbin || (bin == Tbin && !key_greater(dist, idx, Td, Ti));
                 }
                 if (take && P.epipolar) {
-                    const float2 txy = job.t.xy[idx];
-                    const double sd = sampson_dev(P.F, qx, qy, txy.x, txy.y);
+                    const double sd = sampson_dev(P.F, qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
                     if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
                 }
-                unsigned m = __ballot_sync(FULL, take);
-                pairs += __popc(m);
-                while (m) {
-                    const int la = __ffs(m) - 1;
-                    m &= m - 1;
-                    int lb = -1;
-                    if (m) { lb = __ffs(m) - 1; m &= m - 1; }
-                    const int src = (lane < 16) ? la : lb;
-                    const bool cv = src >= 0;
-                    const int cidx = __shfl_sync(FULL, idx, cv ? src : 0);
-                    const float cdist = __shfl_sync(FULL, dist, cv ? src : 0);
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (cv) v = __ldg(reinterpret_cast<const uint4*>(job.t.desc + (size_t)cidx * VISO_DESC_U16) + h);
-                    unsigned acc = __vminu2(qd.x, v.x) + __vminu2(qd.y, v.y) + __vminu2(qd.z, v.z);
-                    if (h != 15) acc += __vminu2(qd.w, v.w);
-                    unsigned s = (acc & 0xffffu) + (acc >> 16);
-                    s += __shfl_xor_sync(FULL, s, 8);
-                    s += __shfl_xor_sync(FULL, s, 4);
-                    s += __shfl_xor_sync(FULL, s, 2);
-                    s += __shfl_xor_sync(FULL, s, 1);
-                    const unsigned tsum = __shfl_sync(FULL, v.w, (lane & 16) | 15);
-                    const int sad = (int)(qsum + tsum - 2u * s);
-                    if (cv) {
-                        if (sad < b1) { b2 = b1; b1 = sad; bdist = cdist; bidx = cidx; }
-                        else if (sad == b1) { b2 = b1; if (key_greater(cdist, cidx, bdist, bidx)) { bdist = cdist; bidx = cidx; } }
-                        else if (sad < b2) b2 = sad;
-                    }
+                const unsigned tm = __ballot_sync(FULL, take);
+                if (tm == 0) return;
+                pairs_ref += __popc(tm);
+                unsigned key = 0xffffffffu; /* (LB << 5 | lane), alive lanes only */
+                if (take) {
+                    const uint4 ta = __ldg(job.t.spsum + 2 * pos), tb = __ldg(job.t.spsum + 2 * pos + 1);
+                    const unsigned s0 = __vminu2(qa.x, ta.x) + __vminu2(qa.y, ta.y) + __vminu2(qa.z, ta.z) + __vminu2(qa.w, ta.w);
+                    const unsigned s1 = __vminu2(qb.x, tb.x) + __vminu2(qb.y, tb.y) + __vminu2(qb.z, tb.z) + __vminu2(qb.w, tb.w);
+                    const unsigned sm = (s0 & 0xffffu) + (s0 >> 16) + (s1 & 0xffffu) + (s1 >> 16);
+                    const unsigned lb = qsum + rec.w - 2u * sm;
+                    key = (lb << 5) | (unsigned)lane;
                 }
-            });
-        }
-        /* merge the two half-warp states */
-        {
-            const int ob1 = __shfl_sync(FULL, b1, 16), ob2 = __shfl_sync(FULL, b2, 16), oidx = __shfl_sync(FULL, bidx, 16);
-            const float odist = __shfl_sync(FULL, bdist, 16);
-            const int hi1 = max(b1, ob1), lo2 = min(b2, ob2);
-            if (ob1 < b1 || (ob1 == b1 && oidx >= 0 && key_greater(odist, oidx, bdist, bidx))) { bidx = oidx; bdist = odist; }
-            b1 = min(b1, ob1);
-            b2 = min(hi1, lo2);
+                while (true) {
+                    /* alive: LB <= current second best (a candidate with SAD > b2 changes nothing) */
+                    const unsigned lim = (b2 == INT_MAX) ? 0xffffffe0u : (((unsigned)b2 << 5) | 31u);
+                    const unsigned k = __reduce_min_sync(FULL, key <= lim ? key : 0xffffffffu);
+                    if (k == 0xffffffffu) break;
+                    const int src = (int)(k & 31u);
+                    if (lane == src) key = 0xffffffffu;
+                    const int cidx = __shfl_sync(FULL, idx, src);
+                    const float cdist = __shfl_sync(FULL, dist, src);
+                    const unsigned tsum = __shfl_sync(FULL, rec.w, src);
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(job.t.desc + (size_t)cidx * VISO_DESC_U16) + lane);
+                    const unsigned acc = __vminu2(qd.x, v.x) + __vminu2(qd.y, v.y);
+                    const unsigned s = __reduce_add_sync(FULL, (acc & 0xffffu) + (acc >> 16));
+                    const int sad = (int)(qsum + tsum - 2u * s);
+                    ++pairs_eval;
+                    if (sad < b1) { b2 = b1; b1 = sad; bdist = cdist; bidx = cidx; }
+                    else if (sad == b1) { b2 = b1; if (key_greater(cdist, cidx, bdist, bidx)) { bdist = cdist; bidx = cidx; } }
+                    else if (sad < b2) b2 = sad;
+                }
+            };
+            if (rows_ready) {
+                visit_rows(job.t, geom, total0, ws, lane, final_chunk);
+            } else {
+                visit_all(job.t, g, geom, ws, lane, final_chunk);
+            }
         }
         if (lane == 0) {
             int valid = 0;
@@ -456,9 +493,9 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
             job.out[q] = make_int4(bidx, b1, b2, valid);
         }
     }
-    if (sad_pairs) {
-        pairs = __shfl_sync(FULL, pairs, 0);
-        if (lane == 0 && pairs) atomicAdd(sad_pairs, pairs);
+    if (sad_pairs && lane == 0 && (pairs_ref | pairs_eval)) {
+        atomicAdd(sad_pairs, (unsigned long long)pairs_ref);
+        atomicAdd(sad_pairs + 1, (unsigned long long)pairs_eval);
     }
 }
 
@@ -469,10 +506,19 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
  * (viso.cpp:711-722), (2) the reference's std::sort order (viso.cpp:724) via the restated libstdc++ introsort
  * run by one thread, (3) pos_of_query inverse table, collect_matches (viso.cpp:501-514) and
  * triangulate_rectified<double> (viso.cpp:1146-1152).
+ *
+ * The sort is sequential by nature (the permutation of equal-distance matches is a property of libstdc++'s
+ * algorithm), so it is made cheap instead: when the frame's matches fit the CTA's shared memory (smem_cap of
+ * them, 20 bytes each) one thread sorts 8-byte (dist, position) records there -- the algorithm only looks at dist,
+ * so the resulting permutation is the one std::sort gives the Match vector -- and the CTA then applies it.
+ * Larger inputs are sorted in place in global memory.
  */
-__global__ void __launch_bounds__(256) compact_sort_kernel(const SortJob* __restrict__ jobs, ParamDev P)
+__global__ void __launch_bounds__(256) compact_sort_kernel(const SortJob* __restrict__ jobs, ParamDev P, int smem_cap)
 {
+    extern __shared__ int sort_sm[];
     __shared__ int warp_tot[32];
+    viso_sort::KV* kv = reinterpret_cast<viso_sort::KV*>(sort_sm);          /* [smem_cap] */
+    int* stage = sort_sm + 2 * smem_cap;                                      /* [smem_cap][3] */
     const SortJob job = jobs[blockIdx.x];
     const int n = *job.n;
     int base = 0;
@@ -486,20 +532,33 @@ __global__ void __launch_bounds__(256) compact_sort_kernel(const SortJob* __rest
         const bool flag = i < n && r.w != 0;
         const int slot = block_compact_slot(flag, base, warp_tot);
         if (flag) {
+            if (slot < smem_cap) {
+                kv[slot].d = r.y; kv[slot].pos = slot;
+                stage[3 * slot + 0] = i; stage[3 * slot + 1] = r.x; stage[3 * slot + 2] = r.y;
+            }
             job.matches[3 * slot + 0] = i;
             job.matches[3 * slot + 1] = r.x;
             job.matches[3 * slot + 2] = r.y;
         }
     }
     const int M = base;
+    const bool in_smem = M <= smem_cap;
     __syncthreads();
     if (threadIdx.x == 0) {
-        viso_sort::sort(reinterpret_cast<viso_sort::M3*>(job.matches), M);
+        if (in_smem) viso_sort::sort(kv, M);
+        else viso_sort::sort(reinterpret_cast<viso_sort::M3*>(job.matches), M);
         *job.count = M;
     }
     __syncthreads();
     for (int p = threadIdx.x; p < M; p += blockDim.x) {
-        const int i1 = job.matches[3 * p], i2 = job.matches[3 * p + 1];
+        int i1, i2;
+        if (in_smem) {
+            const int src = kv[p].pos;
+            i1 = stage[3 * src]; i2 = stage[3 * src + 1];
+            job.matches[3 * p] = i1; job.matches[3 * p + 1] = i2; job.matches[3 * p + 2] = stage[3 * src + 2];
+        } else {
+            i1 = job.matches[3 * p]; i2 = job.matches[3 * p + 1];
+        }
         if (job.pos_of_query) job.pos_of_query[i1] = p;
         if (job.x) {
             const float2 a = job.kp1[i1], b = job.kp2[i2];
@@ -1150,10 +1209,18 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, cons
     return cudaGetLastError();
 }
 
-cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, ParamDev p, cudaStream_t s)
+cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, int max_n, ParamDev p, cudaStream_t s)
 {
     if (n_jobs <= 0) return cudaSuccess;
-    compact_sort_kernel<<<n_jobs, 256, 0, s>>>(jobs, p);
+    /* 20 bytes of shared memory per match: (dist,pos) record + staged Match; up to ~200 KB per CTA */
+    int cap = max_n < 1 ? 1 : max_n;
+    if (cap > 10000) cap = 10000;
+    const size_t smem = (size_t)cap * 20;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(compact_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    compact_sort_kernel<<<n_jobs, 256, smem, s>>>(jobs, p, cap);
     return cudaGetLastError();
 }
 

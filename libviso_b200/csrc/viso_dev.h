@@ -4,9 +4,10 @@
  * HBM layout (see DESIGN.md "Data layout"):
  *   keypoints        float2[n]                      original order (index = the reference's keypoint index)
  *   descriptors f32  float[n][desc_len]             the reference's cv::Mat layout (input only)
- *   descriptors u16  uint16[n][128]                 biased (v+1024) Sobel values; elements 126..127 hold the
- *                                                   32-bit row sum; 256 B per row = 16 x uint4
- *   candidate grid   cell_start int[ncell+1], sxy float2[n], sidx int[n]   counting sort by 16-px cell
+ *   descriptors u16  uint16[n][128]                 biased (v+1024) Sobel values, pad elements 0; 256 B per row
+ *   group sums       uint16[n][16] + uint32[n]      sums of the 16 groups of 8 elements, and of the whole row
+ *   candidate grid   cell_start int[ncell+1], srec uint4[n] = (x, y, index, row sum), spsum 32 B[n]
+ *                                                   counting sort by 16-px cell
  *   dense match out  int4[n]                        (best_idx, best_d1, best_d2, valid) per query
  */
 #ifndef VISO_DEV_H_
@@ -27,9 +28,9 @@ struct GridCfg { int gx, gy; };
 struct SetView {
     const float2* xy;        /* original order */
     const int* n;            /* device pointer to the keypoint count */
-    const uint16_t* desc;    /* packed rows */
-    const float2* sxy;       /* cell-sorted coordinates */
-    const int* sidx;         /* cell-sorted -> original index */
+    const uint16_t* desc;    /* packed rows, original order */
+    const uint4* srec;       /* cell-sorted candidate records: (x, y, original index, row sum) */
+    const uint4* spsum;      /* cell-sorted group sums: 2 x uint4 (16 x u16) per point */
     const int* cell_start;   /* ncell+1 */
 };
 
@@ -56,13 +57,17 @@ struct PackJob {
     const float* d;          /* n x dlen float */
     const int* n;
     uint16_t* out;           /* n x 128 u16 */
+    unsigned* psum;          /* n x 8 words: 16 u16 group sums */
+    unsigned* rsum;          /* n row sums */
 };
 
 struct GridJob {
     const float2* xy;
     const int* n;
-    float2* sxy;
-    int* sidx;
+    const unsigned* psum;    /* from pack, original order */
+    const unsigned* rsum;
+    uint4* srec;
+    uint4* spsum;
     int* cell_start;
 };
 
@@ -131,7 +136,7 @@ cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dle
 cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStream_t s);
 cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, const MatchParamsPair& mp, GridCfg g,
                               unsigned long long* sad_pairs, cudaStream_t s);
-cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, ParamDev p, cudaStream_t s);
+cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, int max_n, ParamDev p, cudaStream_t s);
 cudaError_t viso_launch_circle(const CircleJob* jobs, int n_jobs, cudaStream_t s);
 cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, int max_n, ParamDev p, cudaStream_t s,
                                int* launches);

@@ -154,7 +154,7 @@ def extract_descriptors(img, kp, radius=5):
     """viso.cpp:1004-1024 (vectorised). Returns (N,(2r+1)^2) float32."""
     sob = sobel_x(img)
     h, w = img.shape
-    px = kp[:, 0].astype(np.int64); py = kp[:, 1].astype(np.int64)
+    px = np.rint(kp[:, 0]).astype(np.int64); py = np.rint(kp[:, 1]).astype(np.int64)  # Point2i p = kp.pt: cvRound
     offs = np.arange(-radius, radius + 1)
     yy = py[:, None, None] + offs[None, :, None]
     xx = px[:, None, None] + offs[None, None, :]

@@ -628,7 +628,7 @@ void vo_extract_descriptors(const float* sob, int h, int w, const float* kp, int
     /* viso.cpp:1011-1023 */
     const int side = 2 * radius + 1;
     for (int k = 0; k < n; ++k) {
-        int px = (int)kp[2 * k], py = (int)kp[2 * k + 1]; /* Point2i p = kp.pt: saturate_cast rounds; kps are integral */
+        int px = (int)lrintf(kp[2 * k]), py = (int)lrintf(kp[2 * k + 1]); /* Point2i p = kp.pt: saturate_cast<int> = cvRound (half to even) */
         int col = 0;
         for (int i = -radius; i <= radius; i += 1)
             for (int j = -radius; j <= radius; j += 1, ++col) {

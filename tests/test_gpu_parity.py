@@ -385,6 +385,6 @@ def test_sequence_pipeline(ctx, api, oracle, small_sequence):
     seq.run(pg)
     rec2 = seq.download()
     assert rec2.tobytes() == rec.tobytes()
-    mb, pairs = seq.stats()
-    assert mb > 0 and pairs > 0
+    mb, pairs, evaluated = seq.stats()
+    assert mb > 0 and 0 < evaluated <= pairs
     seq.close()
