@@ -295,8 +295,8 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
 
     struct Bufs {
         float2 *xy1, *xy2;
-        uint4 *srec1, *srec2, *sps1, *sps2;
-        unsigned *ps1, *ps2, *rs1, *rs2;
+        uint4 *srec1, *srec2;
+        unsigned *rs1, *rs2;
         float *df1, *df2;
         uint16_t *du1, *du2;
         int *cell1, *cell2, *counts, *err, *matches, *mcount;
@@ -310,8 +310,6 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
     auto carve = [&](Carver& c) {
         b.xy1 = c.take<float2>(n1); b.xy2 = c.take<float2>(n2);
         b.srec1 = c.take<uint4>(n1); b.srec2 = c.take<uint4>(n2);
-        b.sps1 = c.take<uint4>((size_t)n1 * 2); b.sps2 = c.take<uint4>((size_t)n2 * 2);
-        b.ps1 = c.take<unsigned>((size_t)n1 * 8); b.ps2 = c.take<unsigned>((size_t)n2 * 8);
         b.rs1 = c.take<unsigned>(n1); b.rs2 = c.take<unsigned>(n2);
         b.df1 = c.take<float>((size_t)n1 * dlen); b.df2 = c.take<float>((size_t)n2 * dlen);
         b.du1 = c.take<uint16_t>((size_t)n1 * VISO_DESC_U16); b.du2 = c.take<uint16_t>((size_t)n2 * VISO_DESC_U16);
@@ -339,12 +337,11 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
         CK(cudaMemcpyAsync(b.xy2, kp2, (size_t)n2 * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(b.df2, d2, (size_t)n2 * dlen * 4, cudaMemcpyHostToDevice, s));
     }
-    PackJob pj[2] = {{b.df1, b.counts, b.du1, b.ps1, b.rs1}, {b.df2, b.counts + 1, b.du2, b.ps2, b.rs2}};
-    GridJob gj[2] = {{b.xy1, b.counts, b.ps1, b.rs1, b.srec1, b.sps1, b.cell1},
-                     {b.xy2, b.counts + 1, b.ps2, b.rs2, b.srec2, b.sps2, b.cell2}};
+    PackJob pj[2] = {{b.df1, b.counts, b.du1, b.rs1}, {b.df2, b.counts + 1, b.du2, b.rs2}};
+    GridJob gj[2] = {{b.xy1, b.counts, b.rs1, b.srec1, b.cell1}, {b.xy2, b.counts + 1, b.rs2, b.srec2, b.cell2}};
     MatchJob mj;
-    mj.q = SetView{b.xy1, b.counts, b.du1, b.srec1, b.sps1, b.cell1};
-    mj.t = SetView{b.xy2, b.counts + 1, b.du2, b.srec2, b.sps2, b.cell2};
+    mj.q = SetView{b.xy1, b.counts, b.du1, b.srec1, b.cell1};
+    mj.t = SetView{b.xy2, b.counts + 1, b.du2, b.srec2, b.cell2};
     mj.out = b.out; mj.mode = 0; mj.pad = 0;
     SortJob sj;
     sj.dense = b.out; sj.n = b.counts; sj.kp1 = b.xy1; sj.kp2 = b.xy2; sj.matches = b.matches; sj.count = b.mcount;
@@ -854,8 +851,8 @@ struct viso_seq {
     int F = 0, cap = 0, dlen = 0, maxH = 0, ncell = 0;
     GridCfg grid{};
     float2 *kpL = nullptr, *kpR = nullptr;
-    uint4 *srecL = nullptr, *srecR = nullptr, *spsL = nullptr, *spsR = nullptr;
-    unsigned *psL = nullptr, *psR = nullptr, *rsL = nullptr, *rsR = nullptr;
+    uint4 *srecL = nullptr, *srecR = nullptr;
+    unsigned *rsL = nullptr, *rsR = nullptr;
     float *dLf = nullptr, *dRf = nullptr;
     uint16_t *dLu = nullptr, *dRu = nullptr;
     int *nL = nullptr, *nR = nullptr, *cellL = nullptr, *cellR = nullptr;
@@ -930,7 +927,7 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
         }                                                                                \
     } while (0)
     SA(kpL, F * cap); SA(kpR, F * cap); SA(srecL, F * cap); SA(srecR, F * cap);
-    SA(spsL, F * cap * 2); SA(spsR, F * cap * 2); SA(psL, F * cap * 8); SA(psR, F * cap * 8); SA(rsL, F * cap); SA(rsR, F * cap);
+    SA(rsL, F * cap); SA(rsR, F * cap);
     SA(dLf, F * cap * desc_len); SA(dRf, F * cap * desc_len);
     SA(dLu, F * cap * VISO_DESC_U16); SA(dRu, F * cap * VISO_DESC_U16);
     SA(nL, F); SA(nR, F); SA(cellL, F * nc); SA(cellR, F * nc);
@@ -968,21 +965,17 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     s->h_probs.resize(F);
     auto viewL = [&](size_t t) {
         return SetView{s->kpL + t * cap, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->srecL + t * cap,
-                       s->spsL + t * cap * 2, s->cellL + t * nc};
+                       s->cellL + t * nc};
     };
     auto viewR = [&](size_t t) {
         return SetView{s->kpR + t * cap, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->srecR + t * cap,
-                       s->spsR + t * cap * 2, s->cellR + t * nc};
+                       s->cellR + t * nc};
     };
     for (size_t t = 0; t < F; ++t) {
-        pj[2 * t] = PackJob{s->dLf + t * cap * desc_len, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->psL + t * cap * 8,
-                            s->rsL + t * cap};
-        pj[2 * t + 1] = PackJob{s->dRf + t * cap * desc_len, s->nR + t, s->dRu + t * cap * VISO_DESC_U16,
-                                s->psR + t * cap * 8, s->rsR + t * cap};
-        gj[2 * t] = GridJob{s->kpL + t * cap, s->nL + t, s->psL + t * cap * 8, s->rsL + t * cap, s->srecL + t * cap,
-                            s->spsL + t * cap * 2, s->cellL + t * nc};
-        gj[2 * t + 1] = GridJob{s->kpR + t * cap, s->nR + t, s->psR + t * cap * 8, s->rsR + t * cap, s->srecR + t * cap,
-                                s->spsR + t * cap * 2, s->cellR + t * nc};
+        pj[2 * t] = PackJob{s->dLf + t * cap * desc_len, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->rsL + t * cap};
+        pj[2 * t + 1] = PackJob{s->dRf + t * cap * desc_len, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->rsR + t * cap};
+        gj[2 * t] = GridJob{s->kpL + t * cap, s->nL + t, s->rsL + t * cap, s->srecL + t * cap, s->cellL + t * nc};
+        gj[2 * t + 1] = GridJob{s->kpR + t * cap, s->nR + t, s->rsR + t * cap, s->srecR + t * cap, s->cellR + t * nc};
         MatchJob m;
         m.pad = 0;
         m.q = viewL(t); m.t = viewR(t); m.out = s->dense_lr + t * cap; m.mode = 0; /* stereo, viso.cpp:1240 */

@@ -68,10 +68,9 @@ __device__ __forceinline__ int block_compact_slot(bool flag, int& base_io, int* 
 /* ------------------------------------------------------------------------------------------------ pack */
 
 /*
- * f32 cv::Mat descriptor rows (viso.cpp:999-1002) -> biased u16 rows (v + 1024, pad elements 0), plus per row
- *   psum[16]  u16 sums of the 16 groups of 8 consecutive elements (one uint4 of the packed row each)
- *   rsum      u32 sum of the whole packed row
- * One warp per row, lane l owns elements 4l..4l+3.  Also the domain check (integer valued, |v| <= 1023).
+ * f32 cv::Mat descriptor rows (viso.cpp:999-1002) -> biased u16 rows (v + 1024, pad elements 0), plus the u32 sum
+ * of the packed row.  One warp per row, lane l owns elements 4l..4l+3.  Also the domain check (integer valued,
+ * |v| <= 1023).
  */
 __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restrict__ jobs, int dlen, int* err)
 {
@@ -88,7 +87,7 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
             int k = lane * 4 + e;
             unsigned v = 0;
             if (k < dlen) {
-                float f = src[k];
+                float f = __ldg(src + k);
                 float r = truncf(f);
                 if (!(f == r) || !(fabsf(f) <= 1023.f)) bad = 1;
                 else v = (unsigned)((int)r + 1024);
@@ -100,10 +99,6 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
         w.x = u[0] | (u[1] << 16);
         w.y = u[2] | (u[3] << 16);
         reinterpret_cast<uint2*>(job.out + (size_t)row * VISO_DESC_U16)[lane] = w;
-        /* group sums: group p = lanes 2p, 2p+1 */
-        unsigned g = sum + __shfl_xor_sync(FULL, sum, 1);
-        unsigned g2 = __shfl_down_sync(FULL, g, 2);       /* lane 4j: group 2j+1 */
-        if ((lane & 3) == 0) job.psum[(size_t)row * 8 + (lane >> 2)] = g | (g2 << 16);
         const unsigned tot = warp_sum_u(sum);
         if (lane == 0) job.rsum[row] = tot;
         if (bad) atomicOr(err, 1);
@@ -120,7 +115,7 @@ __device__ __forceinline__ int cell_coord(float v, int g)
 
 /*
  * Counting sort of one keypoint set into 16-px cells (one CTA per set).  Emits, in cell order, the candidate
- * records the matcher streams: srec = (x, y, original index, row sum) and the 32-byte group-sum vector.
+ * records the matcher streams: srec = (x, y, original index, row sum).
  */
 __global__ void __launch_bounds__(512) grid_build_kernel(const GridJob* __restrict__ jobs, GridCfg g)
 {
@@ -155,13 +150,10 @@ __global__ void __launch_bounds__(512) grid_build_kernel(const GridJob* __restri
         if (c < ncell) cursor[c] = v;
     }
     __syncthreads();
-    const uint4* ps = reinterpret_cast<const uint4*>(job.psum);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         float2 p = job.xy[i];
         int pos = atomicAdd(&cursor[cell_coord(p.y, g.gy) * g.gx + cell_coord(p.x, g.gx)], 1);
         job.srec[pos] = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), (unsigned)i, job.rsum[i]);
-        job.spsum[2 * pos] = ps[2 * i];
-        job.spsum[2 * pos + 1] = ps[2 * i + 1];
     }
 }
 
@@ -199,6 +191,10 @@ struct WarpScratch {
     unsigned hist[VISO_HIST_BINS];
     float tieD[VISO_TIE_CAP];
     int tieI[VISO_TIE_CAP];
+    /* scanned-candidate list of the current query (phase 1 -> phase 2) */
+    int lidx[VISO_LIST_CAP];
+    float ldist[VISO_LIST_CAP];
+    unsigned lsum[VISO_LIST_CAP];
 };
 
 struct QueryGeom {
@@ -229,8 +225,8 @@ __device__ __forceinline__ int setup_rows(const SetView& t, GridCfg g, const Que
         const float rem = q.r - dymin + q.slack;
         if (rem >= 0.f) {
             const int cx0 = cell_coord(q.qx - rem, g.gx), cx1 = cell_coord(q.qx + rem, g.gx);
-            s0 = t.cell_start[cy * g.gx + cx0];
-            len = t.cell_start[cy * g.gx + cx1 + 1] - s0;
+            s0 = __ldg(t.cell_start + cy * g.gx + cx0);
+            len = __ldg(t.cell_start + cy * g.gx + cx1 + 1) - s0;
         }
     }
     const int incl = warp_incl_scan(len, lane);
@@ -242,8 +238,8 @@ __device__ __forceinline__ int setup_rows(const SetView& t, GridCfg g, const Que
     return __shfl_sync(FULL, incl, 31);
 }
 
-/* Visit the points of the spans prepared by setup_rows, 32 per step: f(in, dist, rec, pos) is called by all lanes;
- * rec = (x, y, original index, row sum) and pos the cell-sorted position of this lane's point. */
+/* Visit the points of the spans prepared by setup_rows, 32 per step: f(in, dist, rec) is called by all lanes;
+ * rec = (x, y, original index, row sum) of this lane's point. */
 template <class Fn>
 __device__ __forceinline__ void visit_rows(const SetView& t, const QueryGeom& q, int total, WarpScratch& ws, int lane, Fn&& f)
 {
@@ -253,14 +249,13 @@ __device__ __forceinline__ void visit_rows(const SetView& t, const QueryGeom& q,
         const bool in = fl < total;
         float dist = CUDART_INF_F;
         uint4 rec = make_uint4(0, 0, 0xffffffffu, 0);
-        int p = 0;
         if (in) {
             while (fl >= ws.rowPre[row + 1]) ++row;
-            p = ws.rowS0[row] + (fl - ws.rowPre[row]);
+            const int p = ws.rowS0[row] + (fl - ws.rowPre[row]);
             rec = __ldg(t.srec + p);
             dist = l1_dist(q.qx, q.qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
         }
-        f(in, dist, rec, p);
+        f(in, dist, rec);
     }
 }
 
@@ -278,8 +273,88 @@ __device__ __forceinline__ int dist_bin(float dist, float scale)
     return min(VISO_HIST_BINS - 1, (int)(dist * scale));
 }
 
+/* running result of one query (warp-uniform values) */
+struct BestState {
+    unsigned b1, b2;     /* smallest / second smallest SAD with multiplicity; 0xffffffff = none */
+    unsigned bdist;      /* float bits of the L1 distance of the best (>= +0, so unsigned order == float order) */
+    int bidx;
+};
+
 /*
- * match_desc, viso.cpp:668-722.  One warp per query; the candidates of a query are visited 32 at a time, one per lane.
+ * Phase 2: exact SAD of the n listed candidates against the query, 32 candidates per batch.
+ *
+ * Eight lanes share one 256-byte descriptor row (32 bytes = 16 elements per lane, two LDG.128 that together with
+ * the other seven lanes cover two full 128-byte lines), four rows per step, eight steps per batch.  Each lane holds
+ * the matching 32-byte segment of the query row in registers (qa, qb).  Per element pair one VIMNMX.U16x2 + one
+ * add:  sum|a-b| = sum(a) + sum(b) - 2*sum(min(a,b)), with the row sums precomputed by the pack kernel.  The
+ * eight per-step partial sums of a lane are then transposed-reduced across the 8 lanes of a row group (7 SHFL), so
+ * that lane (g, sub) ends up with the complete sum for candidate 4*sub + g of the batch, and the batch is folded
+ * into the running (best, second best) with REDUX min/max -- ties on the SAD go to the largest (L1, index) key,
+ * i.e. the last one in the reference's scan order (viso.cpp:703).
+ */
+__device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, const WarpScratch& ws, int n, int lane,
+                                          const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
+{
+    const int sub = lane & 7, g = lane >> 3;
+    const bool b0 = sub & 1, b1 = sub & 2, b2 = sub & 4;
+    for (int base = 0; base < n; base += 32) {
+        const int nb = min(32, n - base);
+        unsigned part[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            part[s] = 0;
+            if (4 * s < nb) { /* warp uniform */
+                const int e = min(base + 4 * s + g, n - 1);
+                const int idx = ws.lidx[e];
+                const uint4* rp = reinterpret_cast<const uint4*>(tdesc + (size_t)idx * VISO_DESC_U16) + sub * 2;
+                const uint4 a = __ldg(rp), b = __ldg(rp + 1);
+                const unsigned acc = __vminu2(qa.x, a.x) + __vminu2(qa.y, a.y) + __vminu2(qa.z, a.z) + __vminu2(qa.w, a.w) +
+                                     __vminu2(qb.x, b.x) + __vminu2(qb.y, b.y) + __vminu2(qb.z, b.z) + __vminu2(qb.w, b.w);
+                part[s] = (acc & 0xffffu) + (acc >> 16); /* 16 elements x 2047 < 65536: no carry between halves */
+            }
+        }
+        /* transposed reduction over the 8 lanes of a row group */
+        unsigned r4[4], r2[2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned lo = part[2 * j], hi = part[2 * j + 1];
+            r4[j] = (b0 ? hi : lo) + __shfl_xor_sync(FULL, b0 ? lo : hi, 1);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const unsigned lo = r4[2 * j], hi = r4[2 * j + 1];
+            r2[j] = (b1 ? hi : lo) + __shfl_xor_sync(FULL, b1 ? lo : hi, 2);
+        }
+        const unsigned tot = (b2 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b2 ? r2[0] : r2[1], 4);
+        /* this lane's candidate */
+        const int e = base + 4 * sub + g;
+        const bool v = e < n;
+        unsigned sad = 0xffffffffu, dbits = 0;
+        int idx = -1;
+        if (v) {
+            sad = qsum + ws.lsum[e] - 2u * tot;
+            dbits = __float_as_uint(ws.ldist[e]);
+            idx = ws.lidx[e];
+        }
+        const unsigned m1 = __reduce_min_sync(FULL, sad);
+        const unsigned ties = __ballot_sync(FULL, sad == m1);
+        unsigned m2 = m1;
+        if (__popc(ties) < 2) m2 = __reduce_min_sync(FULL, sad == m1 ? 0xffffffffu : sad);
+        const unsigned kd = __reduce_max_sync(FULL, sad == m1 ? dbits : 0u);
+        const int ki = __reduce_max_sync(FULL, (sad == m1 && dbits == kd) ? idx : -1);
+        if (m1 < st.b1) {
+            st.b2 = min(st.b1, m2); st.b1 = m1; st.bdist = kd; st.bidx = ki;
+        } else if (m1 == st.b1) {
+            st.b2 = st.b1;
+            if (kd > st.bdist || (kd == st.bdist && ki > st.bidx)) { st.bdist = kd; st.bidx = ki; }
+        } else if (m1 < st.b2) {
+            st.b2 = m1;
+        }
+    }
+}
+
+/*
+ * match_desc, viso.cpp:668-722.  One warp per query.
  *
  * Reference semantics restated set-wise: with D0 = L1(query, target 0) if that is <= radius
  * (else +inf), the scanned candidates are the K smallest keys (L1, index) among
@@ -287,19 +362,15 @@ __device__ __forceinline__ int dist_bin(float dist, float scale)
  * (target 0 terminates the reference's scan, viso.cpp:693, and sorts first inside its distance group, so exactly
  * the strictly closer points are scanned).  Over that set: best = min SAD, ties to the LARGEST key (the last one
  * in scan order, viso.cpp:703), best_d2 = second smallest SAD with multiplicity.  Sampson-gated candidates
- * (viso.cpp:695-701) still occupy a top-K slot but are not compared.  All of it is order independent, which is
- * what allows the exact pruning below.
+ * (viso.cpp:695-701) still occupy a top-K slot but are not compared.  All of it is order independent.
  *
- * SAD on biased u16 rows: sum|a-b| = sum(a) + sum(b) - 2*sum(min(a,b))  (VIMNMX.U16x2 + IADD, REDUX.SUM across the
- * warp, 8 bytes of the 256-byte row per lane).
- *
- * Exact pruning: with the 16 group sums A_p, B_p of a row pair,  LB = sum_p |A_p - B_p| <= SAD  (triangle
- * inequality per group).  LB costs 32 bytes and ~20 instructions per candidate and is evaluated by every lane for
- * its own candidate; a candidate whose LB exceeds the current second-best SAD can change neither best nor
- * second-best and is skipped.  Survivors are evaluated smallest-LB first (CREDUX.MIN picks the lane), so the
- * bounds tighten after the first two and most candidates never have their descriptor row read.
+ * Phase 1 (per query): candidate generation from the 16-px cell grid of the target set -- the spans of the grid rows
+ * under the L1 diamond are visited 32 points at a time (one per lane), the exact top-K cut is found with an 128-bin
+ * histogram over the L1 distance plus an exact rank search inside the cut bin (only when more than K points are in
+ * range), the Sampson gate is applied, and the survivors are appended to a per-warp list in shared memory.
+ * Phase 2: eval_list().
  */
-__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32)
+__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, 3)
 sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, unsigned long long* sad_pairs)
 {
     __shared__ WarpScratch wscr[VISO_MATCH_WARPS];
@@ -311,20 +382,20 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     const float r = P.radius;
     const int K = P.K;
     const float bscale = (float)VISO_HIST_BINS / (r + 1.0f);
-    unsigned pairs_ref = 0, pairs_eval = 0;
+    unsigned pairs_ref = 0;
 
     const int q_end = min(nq, (int)(blockIdx.x + 1) * VISO_MATCH_QPC);
     for (int qi = blockIdx.x * VISO_MATCH_QPC + warp; qi < q_end; qi += VISO_MATCH_WARPS) {
-        /* spatially sorted processing order: neighbouring warps stream the same candidate records */
+        /* spatially sorted processing order: neighbouring warps stream the same candidate rows */
         const uint4 qrec = __ldg(job.q.srec + qi);
         const int q = (int)qrec.z;
         const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
         const unsigned qsum = qrec.w;
-        const uint2 qd = __ldg(reinterpret_cast<const uint2*>(job.q.desc + (size_t)q * VISO_DESC_U16) + lane);
-        const uint4 qa = __ldg(job.q.spsum + 2 * qi), qb = __ldg(job.q.spsum + 2 * qi + 1);
+        const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7) * 2;
+        const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
 
-        int b1 = INT_MAX, b2 = INT_MAX, bidx = -1;
-        float bdist = -1.f;
+        BestState st;
+        st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
 
         if (nt > 0) {
             /* index 0 terminator */
@@ -350,7 +421,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 for (int b = lane; b < VISO_HIST_BINS; b += 32) ws.hist[b] = 0;
                 __syncwarp();
                 int cnt = 0;
-                visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec, int) {
+                visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec) {
                     const bool inL = in && dist <= r && dist < D0;
                     if (inL) atomicAdd(&ws.hist[dist_bin(dist, bscale)], 1u);
                     cnt += __popc(__ballot_sync(FULL, inL));
@@ -382,7 +453,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                     if (m < nb) {
                         if (nb <= VISO_TIE_CAP) {
                             int fill = 0;
-                            visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec, int) {
+                            visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec) {
                                 const bool hitb = in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb;
                                 const unsigned bm = __ballot_sync(FULL, hitb);
                                 if (hitb) {
@@ -410,7 +481,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                             float curD = -1.f; int curI = -1;
                             for (int it = 0; it < m; ++it) {
                                 float bestD = CUDART_INF_F; int bestI = INT_MAX;
-                                visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec, int) {
+                                visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec) {
                                     const int idx = (int)rec.z;
                                     if (in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb &&
                                         key_greater(dist, idx, curD, curI) && key_greater(bestD, bestI, dist, idx)) {
@@ -431,8 +502,11 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 }
             }
 
-            /* final pass: membership, Sampson gate, lower bound, exact SAD of the survivors */
-            auto final_chunk = [&](bool in, float dist, uint4 rec, int pos) {
+            /* final pass: membership, Sampson gate, append to the list; the list is evaluated whenever it may
+             * overflow on the next step and once at the end (membership of a point does not depend on the others
+             * once the threshold is known) */
+            int nlist = 0;
+            auto final_chunk = [&](bool in, float dist, uint4 rec) {
                 const int idx = (int)rec.z;
                 bool take = in && dist <= r && dist < D0;
                 if (take && Tbin != INT_MAX) {
@@ -445,34 +519,17 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 }
                 const unsigned tm = __ballot_sync(FULL, take);
                 if (tm == 0) return;
-                pairs_ref += __popc(tm);
-                unsigned key = 0xffffffffu; /* (LB << 5 | lane), alive lanes only */
                 if (take) {
-                    const uint4 ta = __ldg(job.t.spsum + 2 * pos), tb = __ldg(job.t.spsum + 2 * pos + 1);
-                    const unsigned s0 = __vminu2(qa.x, ta.x) + __vminu2(qa.y, ta.y) + __vminu2(qa.z, ta.z) + __vminu2(qa.w, ta.w);
-                    const unsigned s1 = __vminu2(qb.x, tb.x) + __vminu2(qb.y, tb.y) + __vminu2(qb.z, tb.z) + __vminu2(qb.w, tb.w);
-                    const unsigned sm = (s0 & 0xffffu) + (s0 >> 16) + (s1 & 0xffffu) + (s1 >> 16);
-                    const unsigned lb = qsum + rec.w - 2u * sm;
-                    key = (lb << 5) | (unsigned)lane;
+                    const int o = nlist + __popc(tm & ((1u << lane) - 1));
+                    ws.lidx[o] = idx; ws.ldist[o] = dist; ws.lsum[o] = rec.w;
                 }
-                while (true) {
-                    /* alive: LB <= current second best (a candidate with SAD > b2 changes nothing) */
-                    const unsigned lim = (b2 == INT_MAX) ? 0xffffffe0u : (((unsigned)b2 << 5) | 31u);
-                    const unsigned k = __reduce_min_sync(FULL, key <= lim ? key : 0xffffffffu);
-                    if (k == 0xffffffffu) break;
-                    const int src = (int)(k & 31u);
-                    if (lane == src) key = 0xffffffffu;
-                    const int cidx = __shfl_sync(FULL, idx, src);
-                    const float cdist = __shfl_sync(FULL, dist, src);
-                    const unsigned tsum = __shfl_sync(FULL, rec.w, src);
-                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(job.t.desc + (size_t)cidx * VISO_DESC_U16) + lane);
-                    const unsigned acc = __vminu2(qd.x, v.x) + __vminu2(qd.y, v.y);
-                    const unsigned s = __reduce_add_sync(FULL, (acc & 0xffffu) + (acc >> 16));
-                    const int sad = (int)(qsum + tsum - 2u * s);
-                    ++pairs_eval;
-                    if (sad < b1) { b2 = b1; b1 = sad; bdist = cdist; bidx = cidx; }
-                    else if (sad == b1) { b2 = b1; if (key_greater(cdist, cidx, bdist, bidx)) { bdist = cdist; bidx = cidx; } }
-                    else if (sad < b2) b2 = sad;
+                nlist += __popc(tm);
+                if (nlist > VISO_LIST_CAP - 32) {
+                    __syncwarp();
+                    eval_list(job.t.desc, ws, nlist, lane, qa, qb, qsum, st);
+                    pairs_ref += nlist;
+                    nlist = 0;
+                    __syncwarp();
                 }
             };
             if (rows_ready) {
@@ -480,22 +537,30 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
             } else {
                 visit_all(job.t, g, geom, ws, lane, final_chunk);
             }
+            if (nlist > 0) {
+                __syncwarp();
+                eval_list(job.t.desc, ws, nlist, lane, qa, qb, qsum, st);
+                pairs_ref += nlist;
+                __syncwarp();
+            }
         }
         if (lane == 0) {
             int valid = 0;
-            if (bidx >= 0) {
+            const int b1 = st.bidx >= 0 ? (int)st.b1 : INT_MAX;
+            const int b2 = st.b2 == 0xffffffffu ? INT_MAX : (int)st.b2;
+            if (st.bidx >= 0) {
                 if (P.second_best) {
                     const double d2 = (b2 == INT_MAX) ? 1.7976931348623157e308 : (double)b2;
                     valid = ((double)b1 < d2 * P.ratio) ? 1 : 0; /* viso.cpp:715 */
                 } else
                     valid = 1;
             }
-            job.out[q] = make_int4(bidx, b1, b2, valid);
+            job.out[q] = make_int4(st.bidx, b1, b2, valid);
         }
     }
-    if (sad_pairs && lane == 0 && (pairs_ref | pairs_eval)) {
+    if (sad_pairs && lane == 0 && pairs_ref) {
         atomicAdd(sad_pairs, (unsigned long long)pairs_ref);
-        atomicAdd(sad_pairs + 1, (unsigned long long)pairs_eval);
+        atomicAdd(sad_pairs + 1, (unsigned long long)pairs_ref);
     }
 }
 

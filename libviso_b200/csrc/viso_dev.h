@@ -5,8 +5,8 @@
  *   keypoints        float2[n]                      original order (index = the reference's keypoint index)
  *   descriptors f32  float[n][desc_len]             the reference's cv::Mat layout (input only)
  *   descriptors u16  uint16[n][128]                 biased (v+1024) Sobel values, pad elements 0; 256 B per row
- *   group sums       uint16[n][16] + uint32[n]      sums of the 16 groups of 8 elements, and of the whole row
- *   candidate grid   cell_start int[ncell+1], srec uint4[n] = (x, y, index, row sum), spsum 32 B[n]
+ *   row sums         uint32[n]                      sum of the biased row (SAD = sum a + sum b - 2 sum min(a,b))
+ *   candidate grid   cell_start int[ncell+1], srec uint4[n] = (x, y, index, row sum)
  *                                                   counting sort by 16-px cell
  *   dense match out  int4[n]                        (best_idx, best_d1, best_d2, valid) per query
  */
@@ -20,6 +20,7 @@
 #define VISO_GRID_CS 16          /* candidate grid cell size in pixels (power of two: exact float scaling) */
 #define VISO_HIST_BINS 128
 #define VISO_TIE_CAP 64
+#define VISO_LIST_CAP 128        /* per-warp scanned-candidate list (evaluated and reset when it fills) */
 #define VISO_MATCH_WARPS 8
 #define VISO_MATCH_QPC 32        /* queries per CTA in sad_match */
 
@@ -30,7 +31,6 @@ struct SetView {
     const int* n;            /* device pointer to the keypoint count */
     const uint16_t* desc;    /* packed rows, original order */
     const uint4* srec;       /* cell-sorted candidate records: (x, y, original index, row sum) */
-    const uint4* spsum;      /* cell-sorted group sums: 2 x uint4 (16 x u16) per point */
     const int* cell_start;   /* ncell+1 */
 };
 
@@ -57,17 +57,14 @@ struct PackJob {
     const float* d;          /* n x dlen float */
     const int* n;
     uint16_t* out;           /* n x 128 u16 */
-    unsigned* psum;          /* n x 8 words: 16 u16 group sums */
     unsigned* rsum;          /* n row sums */
 };
 
 struct GridJob {
     const float2* xy;
     const int* n;
-    const unsigned* psum;    /* from pack, original order */
     const unsigned* rsum;
     uint4* srec;
-    uint4* spsum;
     int* cell_start;
 };
 
