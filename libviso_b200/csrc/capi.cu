@@ -356,7 +356,7 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
     mp.p[1] = mp.p[0];
     CK(viso_launch_pack(b.pack, 2, std::max(n1, n2), dlen, b.err, s));
     CK(viso_launch_grid(b.grid, 2, ctx->grid, s));
-    CK(viso_launch_match(b.match, 1, n1, mp, ctx->grid, nullptr, s));
+    CK(viso_launch_match(b.match, 1, n1, n2, mp, ctx->grid, nullptr, s));
     ctx->launches += 3;
     std::vector<int4> host_out;
     std::vector<int> host_m;
@@ -1113,7 +1113,7 @@ int viso_seq_run_resident(viso_seq* s, const viso_param* param)
     CK(viso_launch_pack(s->pack_jobs, 2 * F, max_n, s->dlen, s->err, st));
     CK(viso_launch_grid(s->grid_jobs, 2 * F, s->grid, st));
     CK(cudaEventRecord(s->ev0, st));
-    CK(viso_launch_match(s->match_jobs, 3 * F - 2, max_n, mp, s->grid, s->pairs, st));
+    CK(viso_launch_match(s->match_jobs, 3 * F - 2, max_n, max_n, mp, s->grid, s->pairs, st));
     CK(cudaEventRecord(s->ev1, st));
     CK(viso_launch_sort(s->sort_jobs, F, max_nL, pd, st));
     ctx->launches += (max_n > 0 ? 3 : 1) + 1;

@@ -22,6 +22,7 @@
 #include "introsort.h"
 
 #include <math_constants.h>
+#include <stdlib.h>
 
 #define FULL 0xffffffffu
 
@@ -185,16 +186,20 @@ __device__ __forceinline__ bool key_greater(float d1, int i1, float d2, int i2)
     return d1 > d2 || (d1 == d2 && i1 > i2);
 }
 
+/* per-warp shared scratch.  The top-K threshold search (hist / tie arrays) and the scanned-candidate list are never
+ * live at the same time, so they share storage. */
 struct WarpScratch {
     int rowS0[32];
     int rowPre[33];
-    unsigned hist[VISO_HIST_BINS];
-    float tieD[VISO_TIE_CAP];
-    int tieI[VISO_TIE_CAP];
-    /* scanned-candidate list of the current query (phase 1 -> phase 2) */
-    int lidx[VISO_LIST_CAP];
-    float ldist[VISO_LIST_CAP];
-    unsigned lsum[VISO_LIST_CAP];
+    int pad_[3];
+    union {
+        uint4 list[VISO_LIST_CAP];             /* (target index, L1 distance bits, row sum, -) */
+        struct {
+            unsigned hist[VISO_HIST_BINS];
+            float tieD[VISO_TIE_CAP];
+            int tieI[VISO_TIE_CAP];
+        } sel;
+    };
 };
 
 struct QueryGeom {
@@ -202,71 +207,99 @@ struct QueryGeom {
     int cy0, cy1;
 };
 
+__device__ __forceinline__ float geom_slack(float qx, float qy, float r)
+{
+    return 1.0f + 4e-6f * (fabsf(qx) + fabsf(qy) + r);
+}
+
 __device__ __forceinline__ QueryGeom make_geom(GridCfg g, float qx, float qy, float r)
 {
     QueryGeom q;
     q.qx = qx; q.qy = qy; q.r = r;
-    q.slack = 1.0f + 4e-6f * (fabsf(qx) + fabsf(qy) + r);
+    q.slack = geom_slack(qx, qy, r);
     q.cy0 = cell_coord(qy - r - q.slack, g.gy);
     q.cy1 = cell_coord(qy + r + q.slack, g.gy);
     return q;
 }
 
-/* Spans of the (up to 32) grid rows rg..rg+31 that overlap the L1 diamond: lane l owns row rg+l.  Leaves the
- * flattened prefix table in ws and returns the number of points in those spans (same value in all lanes). */
-__device__ __forceinline__ int setup_rows(const SetView& t, GridCfg g, const QueryGeom& q, int rg, WarpScratch& ws, int lane)
-{
-    const int cy = rg + lane;
-    int s0 = 0, len = 0;
-    if (cy <= q.cy1) {
-        const float lo = (cy == 0) ? -CUDART_INF_F : (float)(cy * VISO_GRID_CS);
-        const float hi = (cy == g.gy - 1) ? CUDART_INF_F : (float)((cy + 1) * VISO_GRID_CS);
-        const float dymin = fmaxf(0.f, fmaxf(lo - q.qy, q.qy - hi));
-        const float rem = q.r - dymin + q.slack;
-        if (rem >= 0.f) {
-            const int cx0 = cell_coord(q.qx - rem, g.gx), cx1 = cell_coord(q.qx + rem, g.gx);
-            s0 = __ldg(t.cell_start + cy * g.gx + cx0);
-            len = __ldg(t.cell_start + cy * g.gx + cx1 + 1) - s0;
+/* ---- candidate visitors: f(in, dist, rec) is called by all lanes of the warp, 32 points per call;
+ *      rec = (x, y, original index, row sum) of this lane's point, dist its L1 distance to the query ---- */
+
+/* Generic visitor: walks the spans of the target grid rows under the L1 diamond straight from global memory.
+ * Handles any radius / point count. */
+struct GlobalVisitor {
+    const SetView& t;
+    GridCfg g;
+    QueryGeom q;
+    WarpScratch& ws;
+    int lane;
+    int total0;
+    bool one_group;
+
+    /* Spans of the (up to 32) grid rows rg..rg+31 that overlap the diamond: lane l owns row rg+l.  Leaves the
+     * flattened prefix table in ws and returns the number of points in those spans (same value in all lanes). */
+    __device__ __forceinline__ int setup_rows(int rg)
+    {
+        const int cy = rg + lane;
+        int s0 = 0, len = 0;
+        if (cy <= q.cy1) {
+            const float lo = (cy == 0) ? -CUDART_INF_F : (float)(cy * VISO_GRID_CS);
+            const float hi = (cy == g.gy - 1) ? CUDART_INF_F : (float)((cy + 1) * VISO_GRID_CS);
+            const float dymin = fmaxf(0.f, fmaxf(lo - q.qy, q.qy - hi));
+            const float rem = q.r - dymin + q.slack;
+            if (rem >= 0.f) {
+                const int cx0 = cell_coord(q.qx - rem, g.gx), cx1 = cell_coord(q.qx + rem, g.gx);
+                s0 = __ldg(t.cell_start + cy * g.gx + cx0);
+                len = __ldg(t.cell_start + cy * g.gx + cx1 + 1) - s0;
+            }
+        }
+        const int incl = warp_incl_scan(len, lane);
+        __syncwarp();
+        ws.rowS0[lane] = s0;
+        ws.rowPre[lane] = incl - len;
+        if (lane == 31) ws.rowPre[32] = incl;
+        __syncwarp();
+        return __shfl_sync(FULL, incl, 31);
+    }
+
+    /* upper bound on the in-radius count: the number of points in the visited spans */
+    __device__ __forceinline__ int bound()
+    {
+        one_group = q.cy1 - q.cy0 < 32;
+        total0 = setup_rows(q.cy0);
+        int b = total0;
+        if (!one_group)
+            for (int rg = q.cy0 + 32; rg <= q.cy1; rg += 32) b += setup_rows(rg);
+        return b;
+    }
+
+    template <class Fn> __device__ __forceinline__ void rows(int total, Fn&& f)
+    {
+        int row = 0;
+        for (int base = 0; base < total; base += 32) {
+            const int fl = base + lane;
+            const bool in = fl < total;
+            float dist = CUDART_INF_F;
+            uint4 rec = make_uint4(0, 0, 0xffffffffu, 0);
+            if (in) {
+                while (fl >= ws.rowPre[row + 1]) ++row;
+                const int p = ws.rowS0[row] + (fl - ws.rowPre[row]);
+                rec = __ldg(t.srec + p);
+                dist = l1_dist(q.qx, q.qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
+            }
+            f(in, dist, rec);
         }
     }
-    const int incl = warp_incl_scan(len, lane);
-    __syncwarp();
-    ws.rowS0[lane] = s0;
-    ws.rowPre[lane] = incl - len;
-    if (lane == 31) ws.rowPre[32] = incl;
-    __syncwarp();
-    return __shfl_sync(FULL, incl, 31);
-}
 
-/* Visit the points of the spans prepared by setup_rows, 32 per step: f(in, dist, rec) is called by all lanes;
- * rec = (x, y, original index, row sum) of this lane's point. */
-template <class Fn>
-__device__ __forceinline__ void visit_rows(const SetView& t, const QueryGeom& q, int total, WarpScratch& ws, int lane, Fn&& f)
-{
-    int row = 0;
-    for (int base = 0; base < total; base += 32) {
-        const int fl = base + lane;
-        const bool in = fl < total;
-        float dist = CUDART_INF_F;
-        uint4 rec = make_uint4(0, 0, 0xffffffffu, 0);
-        if (in) {
-            while (fl >= ws.rowPre[row + 1]) ++row;
-            const int p = ws.rowS0[row] + (fl - ws.rowPre[row]);
-            rec = __ldg(t.srec + p);
-            dist = l1_dist(q.qx, q.qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
+    template <class Fn> __device__ __forceinline__ void all(Fn&& f)
+    {
+        if (one_group) { rows(total0, f); return; } /* the row table of the only group is still in place */
+        for (int rg = q.cy0; rg <= q.cy1; rg += 32) {
+            const int total = setup_rows(rg);
+            rows(total, f);
         }
-        f(in, dist, rec);
     }
-}
-
-template <class Fn>
-__device__ __forceinline__ void visit_all(const SetView& t, GridCfg g, const QueryGeom& q, WarpScratch& ws, int lane, Fn&& f)
-{
-    for (int rg = q.cy0; rg <= q.cy1; rg += 32) {
-        const int total = setup_rows(t, g, q, rg, ws, lane);
-        visit_rows(t, q, total, ws, lane, f);
-    }
-}
+};
 
 __device__ __forceinline__ int dist_bin(float dist, float scale)
 {
@@ -292,29 +325,36 @@ struct BestState {
  * into the running (best, second best) with REDUX min/max -- ties on the SAD go to the largest (L1, index) key,
  * i.e. the last one in the reference's scan order (viso.cpp:703).
  */
-__device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, const WarpScratch& ws, int n, int lane,
-                                          const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
+/* one batch of NS*4 candidates starting at list entry `base` (NS = 8: up to 32, NS = 4: up to 16).  Branch free:
+ * entries past the end of the list are clamped to the last one (a repeated L1-hit load) and masked afterwards, so
+ * that all 2*NS row loads of the batch can be in flight together. */
+template <int NS>
+__device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, const WarpScratch& ws, int base, int n, int lane,
+                                           const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
 {
     const int sub = lane & 7, g = lane >> 3;
     const bool b0 = sub & 1, b1 = sub & 2, b2 = sub & 4;
-    for (int base = 0; base < n; base += 32) {
-        const int nb = min(32, n - base);
-        unsigned part[8];
+    uint4 ra[NS], rb[NS];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            part[s] = 0;
-            if (4 * s < nb) { /* warp uniform */
-                const int e = min(base + 4 * s + g, n - 1);
-                const int idx = ws.lidx[e];
-                const uint4* rp = reinterpret_cast<const uint4*>(tdesc + (size_t)idx * VISO_DESC_U16) + sub * 2;
-                const uint4 a = __ldg(rp), b = __ldg(rp + 1);
-                const unsigned acc = __vminu2(qa.x, a.x) + __vminu2(qa.y, a.y) + __vminu2(qa.z, a.z) + __vminu2(qa.w, a.w) +
-                                     __vminu2(qb.x, b.x) + __vminu2(qb.y, b.y) + __vminu2(qb.z, b.z) + __vminu2(qb.w, b.w);
-                part[s] = (acc & 0xffffu) + (acc >> 16); /* 16 elements x 2047 < 65536: no carry between halves */
-            }
-        }
-        /* transposed reduction over the 8 lanes of a row group */
-        unsigned r4[4], r2[2];
+    for (int s = 0; s < NS; ++s) {
+        const int e = min(base + 4 * s + g, n - 1);
+        const unsigned idx = ws.list[e].x;
+        const uint4* rp = tbase + (size_t)idx * (VISO_DESC_U16 / 8);
+        ra[s] = __ldg(rp);
+        rb[s] = __ldg(rp + 1);
+    }
+    unsigned part[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const unsigned acc = __vminu2(qa.x, ra[s].x) + __vminu2(qa.y, ra[s].y) + __vminu2(qa.z, ra[s].z) + __vminu2(qa.w, ra[s].w) +
+                             __vminu2(qb.x, rb[s].x) + __vminu2(qb.y, rb[s].y) + __vminu2(qb.z, rb[s].z) + __vminu2(qb.w, rb[s].w);
+        part[s] = (acc & 0xffffu) + (acc >> 16); /* 16 elements x 2047 < 65536: no carry between halves */
+    }
+    /* transposed reduction over the 8 lanes of a row group: lane (g, sub) ends with candidate 4*step + g where
+     * step = sub (NS = 8) or sub & 3 (NS = 4; lanes sub and sub^4 then hold the same candidate) */
+    unsigned r2[2];
+    if (NS == 8) {
+        unsigned r4[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const unsigned lo = part[2 * j], hi = part[2 * j + 1];
@@ -325,36 +365,74 @@ __device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, co
             const unsigned lo = r4[2 * j], hi = r4[2 * j + 1];
             r2[j] = (b1 ? hi : lo) + __shfl_xor_sync(FULL, b1 ? lo : hi, 2);
         }
-        const unsigned tot = (b2 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b2 ? r2[0] : r2[1], 4);
-        /* this lane's candidate */
-        const int e = base + 4 * sub + g;
-        const bool v = e < n;
-        unsigned sad = 0xffffffffu, dbits = 0;
-        int idx = -1;
-        if (v) {
-            sad = qsum + ws.lsum[e] - 2u * tot;
-            dbits = __float_as_uint(ws.ldist[e]);
-            idx = ws.lidx[e];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const unsigned lo = part[2 * j], hi = part[2 * j + 1];
+            r2[j] = (b0 ? hi : lo) + __shfl_xor_sync(FULL, b0 ? lo : hi, 1);
         }
-        const unsigned m1 = __reduce_min_sync(FULL, sad);
-        const unsigned ties = __ballot_sync(FULL, sad == m1);
-        unsigned m2 = m1;
-        if (__popc(ties) < 2) m2 = __reduce_min_sync(FULL, sad == m1 ? 0xffffffffu : sad);
-        const unsigned kd = __reduce_max_sync(FULL, sad == m1 ? dbits : 0u);
-        const int ki = __reduce_max_sync(FULL, (sad == m1 && dbits == kd) ? idx : -1);
-        if (m1 < st.b1) {
-            st.b2 = min(st.b1, m2); st.b1 = m1; st.bdist = kd; st.bidx = ki;
-        } else if (m1 == st.b1) {
-            st.b2 = st.b1;
-            if (kd > st.bdist || (kd == st.bdist && ki > st.bidx)) { st.bdist = kd; st.bidx = ki; }
-        } else if (m1 < st.b2) {
-            st.b2 = m1;
-        }
+    }
+    unsigned tot;
+    int e;
+    if (NS == 8) {
+        tot = (b2 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b2 ? r2[0] : r2[1], 4);
+        e = base + 4 * sub + g;
+    } else {
+        const unsigned t2 = (b1 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b1 ? r2[0] : r2[1], 2);
+        tot = t2 + __shfl_xor_sync(FULL, t2, 4);
+        e = b2 ? n : base + 4 * (sub & 3) + g; /* the duplicate lanes sit out */
+    }
+    unsigned sad = 0xffffffffu, dbits = 0;
+    int idx = -1;
+    if (e < n) {
+        const uint4 le = ws.list[e];
+        sad = qsum + le.z - 2u * tot;
+        dbits = le.y;
+        idx = (int)le.x;
+    }
+    const unsigned m1 = __reduce_min_sync(FULL, sad);
+    const unsigned ties = __ballot_sync(FULL, sad == m1);
+    unsigned m2 = m1;
+    if (__popc(ties) < 2) m2 = __reduce_min_sync(FULL, sad == m1 ? 0xffffffffu : sad);
+    const unsigned kd = __reduce_max_sync(FULL, sad == m1 ? dbits : 0u);
+    const int ki = __reduce_max_sync(FULL, (sad == m1 && dbits == kd) ? idx : -1);
+    if (m1 < st.b1) {
+        st.b2 = min(st.b1, m2); st.b1 = m1; st.bdist = kd; st.bidx = ki;
+    } else if (m1 == st.b1) {
+        st.b2 = st.b1;
+        if (kd > st.bdist || (kd == st.bdist && ki > st.bidx)) { st.bdist = kd; st.bidx = ki; }
+    } else if (m1 < st.b2) {
+        st.b2 = m1;
     }
 }
 
+__device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, const WarpScratch& ws, int n, int lane,
+                                          const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
+{
+    const uint4* tbase = reinterpret_cast<const uint4*>(tdesc) + (lane & 7) * 2;
+    int base = 0;
+    for (; n - base > 16; base += 32) eval_batch<8>(tbase, ws, base, n, lane, qa, qb, qsum, st);
+    if (base < n) eval_batch<4>(tbase, ws, base, n, lane, qa, qb, qsum, st);
+}
+
+/* viso.cpp:711-722: the ratio test and the dense output record (best_idx, best_d1, best_d2, valid) */
+__device__ __forceinline__ void write_result(const MatchJob& job, const MatchParamsDev& P, int q, const BestState& st)
+{
+    int valid = 0;
+    const int b1 = st.bidx >= 0 ? (int)st.b1 : INT_MAX;
+    const int b2 = st.b2 == 0xffffffffu ? INT_MAX : (int)st.b2;
+    if (st.bidx >= 0) {
+        if (P.second_best) {
+            const double d2 = (b2 == INT_MAX) ? 1.7976931348623157e308 : (double)b2;
+            valid = ((double)b1 < d2 * P.ratio) ? 1 : 0; /* viso.cpp:715 */
+        } else
+            valid = 1;
+    }
+    job.out[q] = make_int4(st.bidx, b1, b2, valid);
+}
+
 /*
- * match_desc, viso.cpp:668-722.  One warp per query.
+ * match_desc for one query, viso.cpp:686-722, by one warp.
  *
  * Reference semantics restated set-wise: with D0 = L1(query, target 0) if that is <= radius
  * (else +inf), the scanned candidates are the K smallest keys (L1, index) among
@@ -364,14 +442,369 @@ __device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, co
  * in scan order, viso.cpp:703), best_d2 = second smallest SAD with multiplicity.  Sampson-gated candidates
  * (viso.cpp:695-701) still occupy a top-K slot but are not compared.  All of it is order independent.
  *
- * Phase 1 (per query): candidate generation from the 16-px cell grid of the target set -- the spans of the grid rows
- * under the L1 diamond are visited 32 points at a time (one per lane), the exact top-K cut is found with an 128-bin
- * histogram over the L1 distance plus an exact rank search inside the cut bin (only when more than K points are in
- * range), the Sampson gate is applied, and the survivors are appended to a per-warp list in shared memory.
- * Phase 2: eval_list().
+ * Phase 1: candidate generation through the visitor V (32 points per step, one per lane); when more than K points
+ * can be in range the exact top-K cut is found with a 128-bin histogram over the L1 distance plus an exact rank
+ * search inside the cut bin; the Sampson gate is applied and the survivors are appended to the per-warp list.
+ * Phase 2: eval_list() whenever the list may overflow on the next step, and once at the end.
+ * Returns the number of (query, candidate) pairs that reached the SAD.
  */
-__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, 3)
-sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, unsigned long long* sad_pairs)
+template <class V>
+__device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, const MatchParamsDev& P, WarpScratch& ws,
+                                                int lane, const uint4 qrec)
+{
+    const int q = (int)qrec.z;
+    const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
+    const unsigned qsum = qrec.w;
+    const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7) * 2;
+    const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
+    const float r = P.radius;
+    const int K = P.K;
+    const float bscale = (float)VISO_HIST_BINS / (r + 1.0f);
+    unsigned pairs = 0;
+
+    BestState st;
+    st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
+
+    /* index 0 terminator */
+    const float2 t0 = __ldg(job.t.xy);
+    const float d0 = l1_dist(qx, qy, t0.x, t0.y);
+    const float D0 = (d0 <= r) ? d0 : CUDART_INF_F;
+
+    /* top-K threshold: (Tbin, Td, Ti); candidates with bin < Tbin, or bin == Tbin and key <= (Td,Ti) */
+    int Tbin = INT_MAX;
+    float Td = CUDART_INF_F;
+    int Ti = INT_MAX;
+    if (vis.bound() > K) {
+        for (int b = lane; b < VISO_HIST_BINS; b += 32) ws.sel.hist[b] = 0;
+        __syncwarp();
+        int cnt = 0;
+        vis.all([&](bool in, float dist, uint4 rec) {
+            const bool inL = in && dist <= r && dist < D0;
+            if (inL) atomicAdd(&ws.sel.hist[dist_bin(dist, bscale)], 1u);
+            cnt += __popc(__ballot_sync(FULL, inL));
+        });
+        __syncwarp();
+        if (cnt > K) {
+            /* find the bin where the cumulative count reaches K */
+            unsigned c[4];
+            unsigned s = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { c[e] = ws.sel.hist[lane * 4 + e]; s += c[e]; }
+            const int incl = warp_incl_scan((int)s, lane);
+            const unsigned hit = __ballot_sync(FULL, incl >= K);
+            const int hl = __ffs(hit) - 1;
+            int tb = 0, before = 0;
+            if (lane == hl) {
+                int run = incl - (int)s;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (run + (int)c[e] >= K) { tb = lane * 4 + e; before = run; break; }
+                    run += (int)c[e];
+                }
+            }
+            tb = __shfl_sync(FULL, tb, hl);
+            before = __shfl_sync(FULL, before, hl);
+            const int nb = (int)ws.sel.hist[tb];
+            const int m = K - before; /* 1..nb keys of bin tb are kept */
+            Tbin = tb;
+            if (m < nb) {
+                if (nb <= VISO_TIE_CAP) {
+                    int fill = 0;
+                    vis.all([&](bool in, float dist, uint4 rec) {
+                        const bool hitb = in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb;
+                        const unsigned bm = __ballot_sync(FULL, hitb);
+                        if (hitb) {
+                            const int o = fill + __popc(bm & ((1u << lane) - 1));
+                            ws.sel.tieD[o] = dist;
+                            ws.sel.tieI[o] = (int)rec.z;
+                        }
+                        fill += __popc(bm);
+                    });
+                    __syncwarp();
+                    /* the key of rank m-1 inside the bin */
+                    float selD = 0.f; int selI = 0; bool have = false;
+                    for (int e = lane; e < nb; e += 32) {
+                        const float de = ws.sel.tieD[e]; const int ie = ws.sel.tieI[e];
+                        int rank = 0;
+                        for (int o = 0; o < nb; ++o) rank += key_greater(de, ie, ws.sel.tieD[o], ws.sel.tieI[o]) ? 1 : 0;
+                        if (rank == m - 1) { selD = de; selI = ie; have = true; }
+                    }
+                    const unsigned hm = __ballot_sync(FULL, have);
+                    const int sl = __ffs(hm) - 1;
+                    Td = __shfl_sync(FULL, selD, sl);
+                    Ti = __shfl_sync(FULL, selI, sl);
+                } else {
+                    /* pathological tie bin: m successive minimum searches (exact, slow) */
+                    float curD = -1.f; int curI = -1;
+                    for (int it = 0; it < m; ++it) {
+                        float bestD = CUDART_INF_F; int bestI = INT_MAX;
+                        vis.all([&](bool in, float dist, uint4 rec) {
+                            const int idx = (int)rec.z;
+                            if (in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb &&
+                                key_greater(dist, idx, curD, curI) && key_greater(bestD, bestI, dist, idx)) {
+                                bestD = dist; bestI = idx;
+                            }
+                        });
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float od = __shfl_xor_sync(FULL, bestD, o);
+                            const int oi = __shfl_xor_sync(FULL, bestI, o);
+                            if (key_greater(bestD, bestI, od, oi)) { bestD = od; bestI = oi; }
+                        }
+                        curD = bestD; curI = bestI;
+                    }
+                    Td = curD; Ti = curI;
+                }
+            }
+        }
+        __syncwarp(); /* the selection scratch is dead from here on: its storage becomes the list */
+    }
+
+    /* final pass: membership, Sampson gate, append to the list (membership of a point does not depend on the
+     * others once the threshold is known, so the list can be evaluated and reset at any time) */
+    int nlist = 0;
+    vis.all([&](bool in, float dist, uint4 rec) {
+        const int idx = (int)rec.z;
+        bool take = in && dist <= r && dist < D0;
+        if (take && Tbin != INT_MAX) {
+            const int bin = dist_bin(dist, bscale);
+            take = bin < Tbin || (bin == Tbin && !key_greater(dist, idx, Td, Ti));
+        }
+        if (take && P.epipolar) {
+            const double sd = sampson_dev(P.F, qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
+            if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
+        }
+        const unsigned tm = __ballot_sync(FULL, take);
+        if (tm == 0) return;
+        if (take) ws.list[nlist + __popc(tm & ((1u << lane) - 1))] = make_uint4(rec.z, __float_as_uint(dist), rec.w, 0u);
+        nlist += __popc(tm);
+        if (nlist > VISO_LIST_CAP - 32) {
+            __syncwarp();
+            eval_list(job.t.desc, ws, nlist, lane, qa, qb, qsum, st);
+            pairs += nlist;
+            nlist = 0;
+            __syncwarp();
+        }
+    });
+    if (nlist > 0) {
+        __syncwarp();
+        eval_list(job.t.desc, ws, nlist, lane, qa, qb, qsum, st);
+        pairs += nlist;
+        __syncwarp();
+    }
+
+    if (lane == 0) write_result(job, P, q, st);
+    return pairs;
+}
+
+/*
+ * sad_match_kernel: match_desc (viso.cpp:668-722) for a batch of jobs.  blockIdx.y = job, blockIdx.x = query tile
+ * (VISO_TILE_W x VISO_TILE_H cells of the QUERY set's grid, 96 x 64 px).
+ *
+ * 1. Staging.  The candidate records (x, y, index, row sum) of every target cell that can hold a neighbour of any of
+ *    the tile's queries -- the bounding box of the tile's query coordinates grown by radius + slack, clamped exactly
+ *    like the per-query geometry -- are copied to shared memory, one contiguous span per grid row (coalesced).
+ * 2. Candidate generation, LANE = QUERY.  Every warp walks a quarter of the staged points; the point is a shared
+ *    memory broadcast and each lane tests it against its own query (radius and index-0 terminator), appending hits
+ *    to that query's list (shared-memory counter).  ~9 instructions per 32 (query, point) tests and no ballots.
+ * 3. Evaluation, WARP = QUERY.  The list is gathered into candidate records (Sampson gate for the stereo mode,
+ *    lanes = candidates) and handed to eval_list().
+ * Queries whose neighbourhood holds more than max_neighbors points (the top-K cut is needed) or overflows the list,
+ * and tiles whose neighbourhood does not fit the staging buffer, take the generic path match_query<GlobalVisitor>;
+ * results are identical.
+ */
+__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, VISO_MATCH_MINB)
+sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, int reg_cap, unsigned long long* sad_pairs)
+{
+    extern __shared__ uint4 reg[];                                /* staged neighbourhood, reg_cap records */
+    __shared__ WarpScratch wscr[VISO_MATCH_WARPS];
+    __shared__ unsigned short qlist[32][VISO_QLIST_CAP + 2];      /* +2: odd word stride, lanes = queries write */
+    __shared__ int qcnt[32];
+    __shared__ int row_off[VISO_MAX_REG_ROWS + 1];
+    __shared__ float box_s[5][VISO_MATCH_WARPS];
+
+    const MatchJob job = jobs[blockIdx.y];
+    const MatchParamsDev& P = mp.p[job.mode];
+    const int nq = *job.q.n, nt = *job.t.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpScratch& ws = wscr[warp];
+    const int tiles_x = (g.gx + VISO_TILE_W - 1) / VISO_TILE_W;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    if (ty * VISO_TILE_H >= g.gy || nq <= 0) return;
+
+    /* the tile's queries: one span of the cell-sorted query array per cell row */
+    const int cx_lo = tx * VISO_TILE_W, cx_hi = min(cx_lo + VISO_TILE_W, g.gx);
+    int qtot = 0;
+    int qs[VISO_TILE_H], ql[VISO_TILE_H];
+#pragma unroll
+    for (int rr = 0; rr < VISO_TILE_H; ++rr) {
+        const int cy = ty * VISO_TILE_H + rr;
+        qs[rr] = 0; ql[rr] = 0;
+        if (cy < g.gy) {
+            qs[rr] = __ldg(job.q.cell_start + cy * g.gx + cx_lo);
+            ql[rr] = __ldg(job.q.cell_start + cy * g.gx + cx_hi) - qs[rr];
+        }
+        qtot += ql[rr];
+    }
+    if (qtot == 0) return;
+
+    auto query_rec = [&](int k) {
+        int pos = 0;
+#pragma unroll
+        for (int rr = 0; rr < VISO_TILE_H; ++rr) {
+            if (k >= 0 && k < ql[rr]) pos = qs[rr] + k;
+            k -= ql[rr];
+        }
+        return __ldg(job.q.srec + pos);
+    };
+
+    if (nt <= 0) { /* no targets: every query is unmatched */
+        for (int k = threadIdx.x; k < qtot; k += blockDim.x)
+            job.out[query_rec(k).z] = make_int4(-1, INT_MAX, INT_MAX, 0);
+        return;
+    }
+
+    /* bounding box of the tile's query coordinates (queries outside the image extent are clamped into border
+     * cells, so the cell rectangle is not a bound) */
+    float xmin = CUDART_INF_F, xmax = -CUDART_INF_F, ymin = CUDART_INF_F, ymax = -CUDART_INF_F, amax = 0.f;
+    for (int k = threadIdx.x; k < qtot; k += blockDim.x) {
+        const uint4 qr = query_rec(k);
+        const float x = __uint_as_float(qr.x), y = __uint_as_float(qr.y);
+        xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+        amax = fmaxf(amax, fabsf(x) + fabsf(y));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(FULL, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(FULL, xmax, o));
+        ymin = fminf(ymin, __shfl_xor_sync(FULL, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, o));
+        amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
+    }
+    if (lane == 0) { box_s[0][warp] = xmin; box_s[1][warp] = xmax; box_s[2][warp] = ymin; box_s[3][warp] = ymax; box_s[4][warp] = amax; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < VISO_MATCH_WARPS; ++w) {
+        xmin = fminf(xmin, box_s[0][w]); xmax = fmaxf(xmax, box_s[1][w]);
+        ymin = fminf(ymin, box_s[2][w]); ymax = fmaxf(ymax, box_s[3][w]);
+        amax = fmaxf(amax, box_s[4][w]);
+    }
+    const float r = P.radius;
+    /* grow by radius + the largest per-query slack (make_geom) + a margin far above the float rounding of the sums */
+    const float grow = r + (1.0f + 4e-6f * (amax + r)) + 4e-6f * (amax + r) + 1e-3f;
+    const int rcx0 = cell_coord(xmin - grow, g.gx), rcx1 = cell_coord(xmax + grow, g.gx);
+    const int rcy0 = cell_coord(ymin - grow, g.gy), rcy1 = cell_coord(ymax + grow, g.gy);
+    const int nrows = rcy1 - rcy0 + 1;
+    bool tile_ok = nrows <= VISO_MAX_REG_ROWS && xmin == xmin && ymin == ymin && reg_cap > 0;
+    if (tile_ok) {
+        if (warp == 0) {
+            int run = 0;
+            for (int b = 0; b < nrows; b += 32) {
+                const int rr = b + lane;
+                int len = 0;
+                if (rr < nrows) {
+                    const int cy = rcy0 + rr;
+                    len = __ldg(job.t.cell_start + cy * g.gx + rcx1 + 1) - __ldg(job.t.cell_start + cy * g.gx + rcx0);
+                }
+                const int incl = warp_incl_scan(len, lane);
+                if (rr < nrows) row_off[rr] = run + incl - len;
+                run += __shfl_sync(FULL, incl, 31);
+            }
+            if (lane == 0) row_off[nrows] = run;
+        }
+        __syncthreads();
+        tile_ok = row_off[nrows] <= reg_cap;
+    }
+
+    unsigned pairs = 0;
+    if (!tile_ok) {
+        for (int k = warp; k < qtot; k += VISO_MATCH_WARPS) {
+            const uint4 qrec = query_rec(k);
+            GlobalVisitor vis{job.t, g, make_geom(g, __uint_as_float(qrec.x), __uint_as_float(qrec.y), r), ws, lane, 0, true};
+            pairs += match_query(vis, job, P, ws, lane, qrec);
+        }
+    } else {
+        const int R = row_off[nrows];
+        for (int rr = warp; rr < nrows; rr += VISO_MATCH_WARPS) {
+            const int o = row_off[rr], len = row_off[rr + 1] - o;
+            const uint4* src = job.t.srec + __ldg(job.t.cell_start + (rcy0 + rr) * g.gx + rcx0);
+            for (int i = lane; i < len; i += 32) reg[o + i] = __ldg(src + i);
+        }
+        const float2 t0 = __ldg(job.t.xy);
+        for (int g0 = 0; g0 < qtot; g0 += 32) { /* groups of 32 queries: lane = query */
+            __syncthreads(); /* staging done (first round) / the previous group's lists are consumed */
+            if (threadIdx.x < 32) qcnt[threadIdx.x] = 0;
+            __syncthreads();
+            {
+                const int k = g0 + lane;
+                const bool act = k < qtot;
+                const uint4 qr = query_rec(act ? k : g0);
+                const float qx = __uint_as_float(qr.x), qy = __uint_as_float(qr.y);
+                const float d0 = l1_dist(qx, qy, t0.x, t0.y);
+                /* limit = min(radius, strictly below D0): candidates need dist <= r and dist < D0 (index-0 rule) */
+                const float D0 = (d0 <= r) ? d0 : CUDART_INF_F;
+                const float2* pts = reinterpret_cast<const float2*>(reg);
+#pragma unroll 4
+                for (int i = warp; i < R; i += VISO_MATCH_WARPS) {
+                    const float2 p = pts[2 * i]; /* (x, y) of the uint4 record: broadcast */
+                    const float dist = l1_dist(qx, qy, p.x, p.y);
+                    if (act && dist <= r && dist < D0) {
+                        const int j = atomicAdd(&qcnt[lane], 1);
+                        if (j < VISO_QLIST_CAP) qlist[lane][j] = (unsigned short)i;
+                    }
+                }
+            }
+            __syncthreads();
+            const int gq = min(32, qtot - g0);
+            for (int kk = warp; kk < gq; kk += VISO_MATCH_WARPS) {
+                const uint4 qrec = query_rec(g0 + kk);
+                const int n = qcnt[kk];
+                if (n > VISO_QLIST_CAP || n > P.K) { /* top-K cut or list overflow: generic path */
+                    GlobalVisitor vis{job.t, g, make_geom(g, __uint_as_float(qrec.x), __uint_as_float(qrec.y), r), ws, lane, 0, true};
+                    pairs += match_query(vis, job, P, ws, lane, qrec);
+                    continue;
+                }
+                const int q = (int)qrec.z;
+                const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
+                const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7) * 2;
+                const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
+                BestState st;
+                st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
+                int nlist = 0;
+                for (int base = 0; base < n; base += 32) {
+                    const int e = base + lane;
+                    bool take = e < n;
+                    const uint4 rec = reg[qlist[kk][take ? e : 0]];
+                    const float dist = l1_dist(qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
+                    if (P.epipolar) {
+                        if (take) {
+                            const double sd = sampson_dev(P.F, qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
+                            if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
+                        }
+                        const unsigned tm = __ballot_sync(FULL, take);
+                        if (take) ws.list[nlist + __popc(tm & ((1u << lane) - 1))] = make_uint4(rec.z, __float_as_uint(dist), rec.w, 0u);
+                        nlist += __popc(tm);
+                    } else {
+                        if (take) ws.list[e] = make_uint4(rec.z, __float_as_uint(dist), rec.w, 0u);
+                        nlist = n;
+                    }
+                }
+                __syncwarp();
+                if (nlist > 0) eval_list(job.t.desc, ws, nlist, lane, qa, qb, qrec.w, st);
+                pairs += nlist;
+                __syncwarp();
+                if (lane == 0) write_result(job, P, q, st);
+            }
+        }
+    }
+    if (sad_pairs && lane == 0 && pairs) {
+        atomicAdd(sad_pairs, (unsigned long long)pairs);
+        atomicAdd(sad_pairs + 1, (unsigned long long)pairs);
+    }
+}
+
+/* variant without tile staging: CTA = VISO_STRIP_QPC consecutive cell-sorted queries, every query walks its own
+ * spans in global memory (GlobalVisitor).  Selected with VISO_MATCH_MODE=strip (A/B measurements). */
+__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, VISO_MATCH_MINB)
+sad_match_strip_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, unsigned long long* sad_pairs)
 {
     __shared__ WarpScratch wscr[VISO_MATCH_WARPS];
     const MatchJob job = jobs[blockIdx.y];
@@ -379,188 +812,20 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     const int nq = *job.q.n, nt = *job.t.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch& ws = wscr[warp];
-    const float r = P.radius;
-    const int K = P.K;
-    const float bscale = (float)VISO_HIST_BINS / (r + 1.0f);
-    unsigned pairs_ref = 0;
-
-    const int q_end = min(nq, (int)(blockIdx.x + 1) * VISO_MATCH_QPC);
-    for (int qi = blockIdx.x * VISO_MATCH_QPC + warp; qi < q_end; qi += VISO_MATCH_WARPS) {
-        /* spatially sorted processing order: neighbouring warps stream the same candidate rows */
+    unsigned pairs = 0;
+    const int q_end = min(nq, (int)(blockIdx.x + 1) * VISO_STRIP_QPC);
+    for (int qi = blockIdx.x * VISO_STRIP_QPC + warp; qi < q_end; qi += VISO_MATCH_WARPS) {
         const uint4 qrec = __ldg(job.q.srec + qi);
-        const int q = (int)qrec.z;
-        const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
-        const unsigned qsum = qrec.w;
-        const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7) * 2;
-        const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
-
-        BestState st;
-        st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
-
-        if (nt > 0) {
-            /* index 0 terminator */
-            const float2 t0 = job.t.xy[0];
-            const float d0 = l1_dist(qx, qy, t0.x, t0.y);
-            const float D0 = (d0 <= r) ? d0 : CUDART_INF_F;
-            const QueryGeom geom = make_geom(g, qx, qy, r);
-            const bool one_group = geom.cy1 - geom.cy0 < 32;
-
-            /* upper bound on the in-radius count: the number of points in the visited spans */
-            int total0 = setup_rows(job.t, g, geom, geom.cy0, ws, lane);
-            int bound = total0;
-            if (!one_group)
-                for (int rg = geom.cy0 + 32; rg <= geom.cy1; rg += 32) bound += setup_rows(job.t, g, geom, rg, ws, lane);
-            bool rows_ready = one_group;
-
-            /* top-K threshold: (Tbin, Td, Ti); candidates with bin < Tbin, or bin == Tbin and key <= (Td,Ti) */
-            int Tbin = INT_MAX;
-            float Td = CUDART_INF_F;
-            int Ti = INT_MAX;
-            if (bound > K) {
-                rows_ready = false;
-                for (int b = lane; b < VISO_HIST_BINS; b += 32) ws.hist[b] = 0;
-                __syncwarp();
-                int cnt = 0;
-                visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec) {
-                    const bool inL = in && dist <= r && dist < D0;
-                    if (inL) atomicAdd(&ws.hist[dist_bin(dist, bscale)], 1u);
-                    cnt += __popc(__ballot_sync(FULL, inL));
-                });
-                __syncwarp();
-                if (cnt > K) {
-                    /* find the bin where the cumulative count reaches K */
-                    unsigned c[4];
-                    unsigned s = 0;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { c[e] = ws.hist[lane * 4 + e]; s += c[e]; }
-                    const int incl = warp_incl_scan((int)s, lane);
-                    const unsigned hit = __ballot_sync(FULL, incl >= K);
-                    const int hl = __ffs(hit) - 1;
-                    int tb = 0, before = 0;
-                    if (lane == hl) {
-                        int run = incl - (int)s;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (run + (int)c[e] >= K) { tb = lane * 4 + e; before = run; break; }
-                            run += (int)c[e];
-                        }
-                    }
-                    tb = __shfl_sync(FULL, tb, hl);
-                    before = __shfl_sync(FULL, before, hl);
-                    const int nb = (int)ws.hist[tb];
-                    const int m = K - before; /* 1..nb keys of bin tb are kept */
-                    Tbin = tb;
-                    if (m < nb) {
-                        if (nb <= VISO_TIE_CAP) {
-                            int fill = 0;
-                            visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec) {
-                                const bool hitb = in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb;
-                                const unsigned bm = __ballot_sync(FULL, hitb);
-                                if (hitb) {
-                                    const int o = fill + __popc(bm & ((1u << lane) - 1));
-                                    ws.tieD[o] = dist;
-                                    ws.tieI[o] = (int)rec.z;
-                                }
-                                fill += __popc(bm);
-                            });
-                            __syncwarp();
-                            /* the key of rank m-1 inside the bin */
-                            float selD = 0.f; int selI = 0; bool have = false;
-                            for (int e = lane; e < nb; e += 32) {
-                                const float de = ws.tieD[e]; const int ie = ws.tieI[e];
-                                int rank = 0;
-                                for (int o = 0; o < nb; ++o) rank += key_greater(de, ie, ws.tieD[o], ws.tieI[o]) ? 1 : 0;
-                                if (rank == m - 1) { selD = de; selI = ie; have = true; }
-                            }
-                            const unsigned hm = __ballot_sync(FULL, have);
-                            const int sl = __ffs(hm) - 1;
-                            Td = __shfl_sync(FULL, selD, sl);
-                            Ti = __shfl_sync(FULL, selI, sl);
-                        } else {
-                            /* pathological tie bin: m successive minimum searches (exact, slow) */
-                            float curD = -1.f; int curI = -1;
-                            for (int it = 0; it < m; ++it) {
-                                float bestD = CUDART_INF_F; int bestI = INT_MAX;
-                                visit_all(job.t, g, geom, ws, lane, [&](bool in, float dist, uint4 rec) {
-                                    const int idx = (int)rec.z;
-                                    if (in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb &&
-                                        key_greater(dist, idx, curD, curI) && key_greater(bestD, bestI, dist, idx)) {
-                                        bestD = dist; bestI = idx;
-                                    }
-                                });
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) {
-                                    const float od = __shfl_xor_sync(FULL, bestD, o);
-                                    const int oi = __shfl_xor_sync(FULL, bestI, o);
-                                    if (key_greater(bestD, bestI, od, oi)) { bestD = od; bestI = oi; }
-                                }
-                                curD = bestD; curI = bestI;
-                            }
-                            Td = curD; Ti = curI;
-                        }
-                    }
-                }
-            }
-
-            /* final pass: membership, Sampson gate, append to the list; the list is evaluated whenever it may
-             * overflow on the next step and once at the end (membership of a point does not depend on the others
-             * once the threshold is known) */
-            int nlist = 0;
-            auto final_chunk = [&](bool in, float dist, uint4 rec) {
-                const int idx = (int)rec.z;
-                bool take = in && dist <= r && dist < D0;
-                if (take && Tbin != INT_MAX) {
-                    const int bin = dist_bin(dist, bscale);
-                    take = bin < Tbin || (bin == Tbin && !key_greater(dist, idx, Td, Ti));
-                }
-                if (take && P.epipolar) {
-                    const double sd = sampson_dev(P.F, qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
-                    if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
-                }
-                const unsigned tm = __ballot_sync(FULL, take);
-                if (tm == 0) return;
-                if (take) {
-                    const int o = nlist + __popc(tm & ((1u << lane) - 1));
-                    ws.lidx[o] = idx; ws.ldist[o] = dist; ws.lsum[o] = rec.w;
-                }
-                nlist += __popc(tm);
-                if (nlist > VISO_LIST_CAP - 32) {
-                    __syncwarp();
-                    eval_list(job.t.desc, ws, nlist, lane, qa, qb, qsum, st);
-                    pairs_ref += nlist;
-                    nlist = 0;
-                    __syncwarp();
-                }
-            };
-            if (rows_ready) {
-                visit_rows(job.t, geom, total0, ws, lane, final_chunk);
-            } else {
-                visit_all(job.t, g, geom, ws, lane, final_chunk);
-            }
-            if (nlist > 0) {
-                __syncwarp();
-                eval_list(job.t.desc, ws, nlist, lane, qa, qb, qsum, st);
-                pairs_ref += nlist;
-                __syncwarp();
-            }
+        if (nt <= 0) {
+            if (lane == 0) job.out[qrec.z] = make_int4(-1, INT_MAX, INT_MAX, 0);
+            continue;
         }
-        if (lane == 0) {
-            int valid = 0;
-            const int b1 = st.bidx >= 0 ? (int)st.b1 : INT_MAX;
-            const int b2 = st.b2 == 0xffffffffu ? INT_MAX : (int)st.b2;
-            if (st.bidx >= 0) {
-                if (P.second_best) {
-                    const double d2 = (b2 == INT_MAX) ? 1.7976931348623157e308 : (double)b2;
-                    valid = ((double)b1 < d2 * P.ratio) ? 1 : 0; /* viso.cpp:715 */
-                } else
-                    valid = 1;
-            }
-            job.out[q] = make_int4(st.bidx, b1, b2, valid);
-        }
+        GlobalVisitor vis{job.t, g, make_geom(g, __uint_as_float(qrec.x), __uint_as_float(qrec.y), P.radius), ws, lane, 0, true};
+        pairs += match_query(vis, job, P, ws, lane, qrec);
     }
-    if (sad_pairs && lane == 0 && pairs_ref) {
-        atomicAdd(sad_pairs, (unsigned long long)pairs_ref);
-        atomicAdd(sad_pairs + 1, (unsigned long long)pairs_ref);
+    if (sad_pairs && lane == 0 && pairs) {
+        atomicAdd(sad_pairs, (unsigned long long)pairs);
+        atomicAdd(sad_pairs + 1, (unsigned long long)pairs);
     }
 }
 
@@ -1265,12 +1530,40 @@ cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStr
     return cudaGetLastError();
 }
 
-cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, const MatchParamsPair& mp, GridCfg g,
-                              unsigned long long* sad_pairs, cudaStream_t s)
+cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
+                              GridCfg g, unsigned long long* sad_pairs, cudaStream_t s)
 {
     if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
-    dim3 grid((max_nq + VISO_MATCH_QPC - 1) / VISO_MATCH_QPC, n_jobs);
-    sad_match_kernel<<<grid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs);
+    /* staging capacity for a tile's neighbourhood: twice the expected point count of the grown tile box at the
+     * densest target set, within [256, 6144] records of 16 bytes */
+    const float r = fmaxf(mp.p[0].radius, mp.p[1].radius);
+    const double ext_x = (double)g.gx * VISO_GRID_CS, ext_y = (double)g.gy * VISO_GRID_CS;
+    const double bx = fmin(ext_x, VISO_TILE_W * VISO_GRID_CS + 2.0 * (r + 2) + 2 * VISO_GRID_CS);
+    const double by = fmin(ext_y, VISO_TILE_H * VISO_GRID_CS + 2.0 * (r + 2) + 2 * VISO_GRID_CS);
+    double expect = (double)max_nt * (bx * by) / (ext_x * ext_y);
+    if (!(expect >= 0)) expect = 0;
+    int cap = (int)fmin(6144.0, fmax(256.0, 2.0 * expect + 64.0));
+    cap = (cap + 63) & ~63;
+    const size_t smem = (size_t)cap * sizeof(uint4);
+    static int attr_set = 0;
+    if (smem > 32 * 1024 && !attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 16);
+        if (e != cudaSuccess) return e;
+        attr_set = 1;
+    }
+    static int mode = -1;
+    if (mode < 0) {
+        const char* m = getenv("VISO_MATCH_MODE");
+        mode = (m && m[0] == 's') ? 1 : 0;
+    }
+    if (mode == 1) {
+        dim3 grid((max_nq + VISO_STRIP_QPC - 1) / VISO_STRIP_QPC, n_jobs);
+        sad_match_strip_kernel<<<grid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs);
+        return cudaGetLastError();
+    }
+    const int tiles = ((g.gx + VISO_TILE_W - 1) / VISO_TILE_W) * ((g.gy + VISO_TILE_H - 1) / VISO_TILE_H);
+    dim3 grid(tiles, n_jobs);
+    sad_match_kernel<<<grid, VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, sad_pairs);
     return cudaGetLastError();
 }
 
