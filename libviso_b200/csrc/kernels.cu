@@ -316,9 +316,10 @@ struct BestState {
 /*
  * Phase 2: exact SAD of the n listed candidates against the query, 32 candidates per batch.
  *
- * Eight lanes share one 256-byte descriptor row (32 bytes = 16 elements per lane, two LDG.128 that together with
- * the other seven lanes cover two full 128-byte lines), four rows per step, eight steps per batch.  Each lane holds
- * the matching 32-byte segment of the query row in registers (qa, qb).  Per element pair one VIMNMX.U16x2 + one
+ * Eight lanes share one 256-byte descriptor row: lane `sub` of the group reads the 16-byte chunks sub and 8 + sub,
+ * so each of the two LDG.128 of a step covers exactly one full 128-byte line per row (4 rows = 4 lines per
+ * instruction, no partially used sector); four rows per step, eight steps per batch.  Each lane holds the matching
+ * two chunks of the query row in registers (qa, qb).  Per element pair one VIMNMX.U16x2 + one
  * add:  sum|a-b| = sum(a) + sum(b) - 2*sum(min(a,b)), with the row sums precomputed by the pack kernel.  The
  * eight per-step partial sums of a lane are then transposed-reduced across the 8 lanes of a row group (7 SHFL), so
  * that lane (g, sub) ends up with the complete sum for candidate 4*sub + g of the batch, and the batch is folded
@@ -341,7 +342,7 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
         const unsigned idx = ws.list[e].x;
         const uint4* rp = tbase + (size_t)idx * (VISO_DESC_U16 / 8);
         ra[s] = __ldg(rp);
-        rb[s] = __ldg(rp + 1);
+        rb[s] = __ldg(rp + 8);
     }
     unsigned part[NS];
 #pragma unroll
@@ -409,7 +410,7 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
 __device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, const WarpScratch& ws, int n, int lane,
                                           const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
 {
-    const uint4* tbase = reinterpret_cast<const uint4*>(tdesc) + (lane & 7) * 2;
+    const uint4* tbase = reinterpret_cast<const uint4*>(tdesc) + (lane & 7);
     int base = 0;
     for (; n - base > 16; base += 32) eval_batch<8>(tbase, ws, base, n, lane, qa, qb, qsum, st);
     if (base < n) eval_batch<4>(tbase, ws, base, n, lane, qa, qb, qsum, st);
@@ -455,8 +456,8 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
     const int q = (int)qrec.z;
     const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
     const unsigned qsum = qrec.w;
-    const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7) * 2;
-    const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
+    const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7);
+    const uint4 qa = __ldg(qp), qb = __ldg(qp + 8);
     const float r = P.radius;
     const int K = P.K;
     const float bscale = (float)VISO_HIST_BINS / (r + 1.0f);
@@ -621,7 +622,8 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     __shared__ unsigned short qlist[32][VISO_QLIST_CAP + 2];      /* +2: odd word stride, lanes = queries write */
     __shared__ int qcnt[32];
     __shared__ int row_off[VISO_MAX_REG_ROWS + 1];
-    __shared__ float box_s[5][VISO_MATCH_WARPS];
+    __shared__ int tile_s[4];
+    __shared__ uint4 qrec_s[32];
 
     const MatchJob job = jobs[blockIdx.y];
     const MatchParamsDev& P = mp.p[job.mode];
@@ -664,55 +666,51 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
         return;
     }
 
-    /* bounding box of the tile's query coordinates (queries outside the image extent are clamped into border
-     * cells, so the cell rectangle is not a bound) */
-    float xmin = CUDART_INF_F, xmax = -CUDART_INF_F, ymin = CUDART_INF_F, ymax = -CUDART_INF_F, amax = 0.f;
-    for (int k = threadIdx.x; k < qtot; k += blockDim.x) {
-        const uint4 qr = query_rec(k);
-        const float x = __uint_as_float(qr.x), y = __uint_as_float(qr.y);
-        xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
-        amax = fmaxf(amax, fabsf(x) + fabsf(y));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        xmin = fminf(xmin, __shfl_xor_sync(FULL, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(FULL, xmax, o));
-        ymin = fminf(ymin, __shfl_xor_sync(FULL, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, o));
-        amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
-    }
-    if (lane == 0) { box_s[0][warp] = xmin; box_s[1][warp] = xmax; box_s[2][warp] = ymin; box_s[3][warp] = ymax; box_s[4][warp] = amax; }
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < VISO_MATCH_WARPS; ++w) {
-        xmin = fminf(xmin, box_s[0][w]); xmax = fmaxf(xmax, box_s[1][w]);
-        ymin = fminf(ymin, box_s[2][w]); ymax = fmaxf(ymax, box_s[3][w]);
-        amax = fmaxf(amax, box_s[4][w]);
-    }
+    /* Neighbourhood of the tile (warp 0): bounding box of the tile's query coordinates (queries outside the image
+     * extent are clamped into border cells, so the cell rectangle is not a bound), grown by radius + the largest
+     * per-query slack (make_geom) + a margin far above the float rounding of the sums; then the staged span of
+     * every grid row. */
     const float r = P.radius;
-    /* grow by radius + the largest per-query slack (make_geom) + a margin far above the float rounding of the sums */
-    const float grow = r + (1.0f + 4e-6f * (amax + r)) + 4e-6f * (amax + r) + 1e-3f;
-    const int rcx0 = cell_coord(xmin - grow, g.gx), rcx1 = cell_coord(xmax + grow, g.gx);
-    const int rcy0 = cell_coord(ymin - grow, g.gy), rcy1 = cell_coord(ymax + grow, g.gy);
-    const int nrows = rcy1 - rcy0 + 1;
-    bool tile_ok = nrows <= VISO_MAX_REG_ROWS && xmin == xmin && ymin == ymin && reg_cap > 0;
-    if (tile_ok) {
-        if (warp == 0) {
+    if (warp == 0) {
+        float xmin = CUDART_INF_F, xmax = -CUDART_INF_F, ymin = CUDART_INF_F, ymax = -CUDART_INF_F, amax = 0.f;
+        for (int k = lane; k < qtot; k += 32) {
+            const uint4 qr = query_rec(k);
+            const float x = __uint_as_float(qr.x), y = __uint_as_float(qr.y);
+            xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+            amax = fmaxf(amax, fabsf(x) + fabsf(y));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = fminf(xmin, __shfl_xor_sync(FULL, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(FULL, xmax, o));
+            ymin = fminf(ymin, __shfl_xor_sync(FULL, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, o));
+            amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
+        }
+        const float grow = r + (1.0f + 4e-6f * (amax + r)) + 4e-6f * (amax + r) + 1e-3f;
+        const int cx0 = cell_coord(xmin - grow, g.gx), cx1 = cell_coord(xmax + grow, g.gx);
+        const int cy0 = cell_coord(ymin - grow, g.gy), cy1 = cell_coord(ymax + grow, g.gy);
+        const int nr = cy1 - cy0 + 1;
+        int total = -1; /* -1: no staging */
+        if (nr <= VISO_MAX_REG_ROWS && xmin == xmin && ymin == ymin && reg_cap > 0) {
             int run = 0;
-            for (int b = 0; b < nrows; b += 32) {
+            for (int b = 0; b < nr; b += 32) {
                 const int rr = b + lane;
                 int len = 0;
-                if (rr < nrows) {
-                    const int cy = rcy0 + rr;
-                    len = __ldg(job.t.cell_start + cy * g.gx + rcx1 + 1) - __ldg(job.t.cell_start + cy * g.gx + rcx0);
+                if (rr < nr) {
+                    const int cy = cy0 + rr;
+                    len = __ldg(job.t.cell_start + cy * g.gx + cx1 + 1) - __ldg(job.t.cell_start + cy * g.gx + cx0);
                 }
                 const int incl = warp_incl_scan(len, lane);
-                if (rr < nrows) row_off[rr] = run + incl - len;
+                if (rr < nr) row_off[rr] = run + incl - len;
                 run += __shfl_sync(FULL, incl, 31);
             }
-            if (lane == 0) row_off[nrows] = run;
+            if (lane == 0) row_off[nr] = run;
+            if (run <= reg_cap) total = run;
         }
-        __syncthreads();
-        tile_ok = row_off[nrows] <= reg_cap;
+        if (lane == 0) { tile_s[0] = cx0; tile_s[1] = cy0; tile_s[2] = nr; tile_s[3] = total; }
     }
+    __syncthreads();
+    const int rcx0 = tile_s[0], rcy0 = tile_s[1], nrows = tile_s[2];
+    const bool tile_ok = tile_s[3] >= 0;
 
     unsigned pairs = 0;
     if (!tile_ok) {
@@ -722,7 +720,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
             pairs += match_query(vis, job, P, ws, lane, qrec);
         }
     } else {
-        const int R = row_off[nrows];
+        const int R = tile_s[3];
         for (int rr = warp; rr < nrows; rr += VISO_MATCH_WARPS) {
             const int o = row_off[rr], len = row_off[rr + 1] - o;
             const uint4* src = job.t.srec + __ldg(job.t.cell_start + (rcy0 + rr) * g.gx + rcx0);
@@ -737,6 +735,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 const int k = g0 + lane;
                 const bool act = k < qtot;
                 const uint4 qr = query_rec(act ? k : g0);
+                if (warp == 0) qrec_s[lane] = qr;
                 const float qx = __uint_as_float(qr.x), qy = __uint_as_float(qr.y);
                 const float d0 = l1_dist(qx, qy, t0.x, t0.y);
                 /* limit = min(radius, strictly below D0): candidates need dist <= r and dist < D0 (index-0 rule) */
@@ -755,7 +754,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
             __syncthreads();
             const int gq = min(32, qtot - g0);
             for (int kk = warp; kk < gq; kk += VISO_MATCH_WARPS) {
-                const uint4 qrec = query_rec(g0 + kk);
+                const uint4 qrec = qrec_s[kk];
                 const int n = qcnt[kk];
                 if (n > VISO_QLIST_CAP || n > P.K) { /* top-K cut or list overflow: generic path */
                     GlobalVisitor vis{job.t, g, make_geom(g, __uint_as_float(qrec.x), __uint_as_float(qrec.y), r), ws, lane, 0, true};
@@ -764,8 +763,8 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 }
                 const int q = (int)qrec.z;
                 const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
-                const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7) * 2;
-                const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
+                const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7);
+                const uint4 qa = __ldg(qp), qb = __ldg(qp + 8);
                 BestState st;
                 st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
                 int nlist = 0;
