@@ -302,6 +302,7 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
         int *cell1, *cell2, *counts, *err, *matches, *mcount;
         int4* out;
         unsigned long long* pairs;
+        int* pending;
         PackJob* pack;
         GridJob* grid;
         MatchJob* match;
@@ -318,6 +319,7 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
         b.matches = c.take<int>((size_t)n1 * 3); b.mcount = c.take<int>(1);
         b.out = c.take<int4>(n1);
         b.pairs = c.take<unsigned long long>(1);
+        b.pending = c.take<int>(1);
         b.pack = c.take<PackJob>(2); b.grid = c.take<GridJob>(2); b.match = c.take<MatchJob>(1); b.sort = c.take<SortJob>(1);
     };
     Carver measure(nullptr);
@@ -356,8 +358,9 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
     mp.p[1] = mp.p[0];
     CK(viso_launch_pack(b.pack, 2, std::max(n1, n2), dlen, b.err, s));
     CK(viso_launch_grid(b.grid, 2, ctx->grid, s));
-    CK(viso_launch_match(b.match, 1, n1, n2, mp, ctx->grid, nullptr, s));
-    ctx->launches += 3;
+    int ml = 0;
+    CK(viso_launch_match(b.match, 1, n1, n2, mp, ctx->grid, nullptr, b.pending, s, &ml));
+    ctx->launches += 2 + ml;
     std::vector<int4> host_out;
     std::vector<int> host_m;
     int flags = 0, mcount = 0;
@@ -872,6 +875,7 @@ struct viso_seq {
     RansacProb* probs = nullptr;
     unsigned long long* pairs = nullptr;
     int* err = nullptr;
+    int* pending = nullptr;
     std::vector<int> h_nL, h_nR;
     std::vector<RansacProb> h_probs;
     int H_cur = -1;
@@ -939,7 +943,7 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     SA(hyp_ok, F * H); SA(hyp_count, F * H); SA(inliers, F * cap); SA(active, F * cap);
     SA(rec, F); SA(seeds, F * H * 3);
     SA(pack_jobs, 2 * F); SA(grid_jobs, 2 * F); SA(match_jobs, 3 * F); SA(sort_jobs, F); SA(circ_jobs, F); SA(probs, F);
-    SA(pairs, 2); SA(err, 1);
+    SA(pairs, 2); SA(err, 1); SA(pending, 1);
 #undef SA
     s->h_nL.assign(F, 0);
     s->h_nR.assign(F, 0);
@@ -1113,10 +1117,11 @@ int viso_seq_run_resident(viso_seq* s, const viso_param* param)
     CK(viso_launch_pack(s->pack_jobs, 2 * F, max_n, s->dlen, s->err, st));
     CK(viso_launch_grid(s->grid_jobs, 2 * F, s->grid, st));
     CK(cudaEventRecord(s->ev0, st));
-    CK(viso_launch_match(s->match_jobs, 3 * F - 2, max_n, max_n, mp, s->grid, s->pairs, st));
+    int ml = 0;
+    CK(viso_launch_match(s->match_jobs, 3 * F - 2, max_n, max_n, mp, s->grid, s->pairs, s->pending, st, &ml));
     CK(cudaEventRecord(s->ev1, st));
     CK(viso_launch_sort(s->sort_jobs, F, max_nL, pd, st));
-    ctx->launches += (max_n > 0 ? 3 : 1) + 1;
+    ctx->launches += (max_n > 0 ? 2 : 0) + ml + 1;
     if (F > 1) {
         CK(viso_launch_circle(s->circ_jobs + 1, F - 1, st));
         ctx->launches += 1;

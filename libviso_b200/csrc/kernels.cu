@@ -335,21 +335,24 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
 {
     const int sub = lane & 7, g = lane >> 3;
     const bool b0 = sub & 1, b1 = sub & 2, b2 = sub & 4;
-    uint4 ra[NS], rb[NS];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const int e = min(base + 4 * s + g, n - 1);
-        const unsigned idx = ws.list[e].x;
-        const uint4* rp = tbase + (size_t)idx * (VISO_DESC_U16 / 8);
-        ra[s] = __ldg(rp);
-        rb[s] = __ldg(rp + 8);
-    }
     unsigned part[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const unsigned acc = __vminu2(qa.x, ra[s].x) + __vminu2(qa.y, ra[s].y) + __vminu2(qa.z, ra[s].z) + __vminu2(qa.w, ra[s].w) +
-                             __vminu2(qb.x, rb[s].x) + __vminu2(qb.y, rb[s].y) + __vminu2(qb.z, rb[s].z) + __vminu2(qb.w, rb[s].w);
-        part[s] = (acc & 0xffffu) + (acc >> 16); /* 16 elements x 2047 < 65536: no carry between halves */
+    for (int h = 0; h < NS; h += VISO_EVAL_DEPTH) { /* VISO_EVAL_DEPTH steps = 2*VISO_EVAL_DEPTH row loads in flight */
+        uint4 ra[VISO_EVAL_DEPTH], rb[VISO_EVAL_DEPTH];
+#pragma unroll
+        for (int s = 0; s < VISO_EVAL_DEPTH; ++s) {
+            const int e = min(base + 4 * (h + s) + g, n - 1);
+            const unsigned idx = ws.list[e].x;
+            const uint4* rp = tbase + (size_t)idx * (VISO_DESC_U16 / 8);
+            ra[s] = __ldg(rp);
+            rb[s] = __ldg(rp + 8);
+        }
+#pragma unroll
+        for (int s = 0; s < VISO_EVAL_DEPTH; ++s) {
+            const unsigned acc = __vminu2(qa.x, ra[s].x) + __vminu2(qa.y, ra[s].y) + __vminu2(qa.z, ra[s].z) + __vminu2(qa.w, ra[s].w) +
+                                 __vminu2(qb.x, rb[s].x) + __vminu2(qb.y, rb[s].y) + __vminu2(qb.z, rb[s].z) + __vminu2(qb.w, rb[s].w);
+            part[h + s] = (acc & 0xffffu) + (acc >> 16); /* 16 elements x 2047 < 65536: no carry between halves */
+        }
     }
     /* transposed reduction over the 8 lanes of a row group: lane (g, sub) ends with candidate 4*step + g where
      * step = sub (NS = 8) or sub & 3 (NS = 4; lanes sub and sub^4 then hold the same candidate) */
@@ -611,11 +614,13 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
  * 3. Evaluation, WARP = QUERY.  The list is gathered into candidate records (Sampson gate for the stereo mode,
  *    lanes = candidates) and handed to eval_list().
  * Queries whose neighbourhood holds more than max_neighbors points (the top-K cut is needed) or overflows the list,
- * and tiles whose neighbourhood does not fit the staging buffer, take the generic path match_query<GlobalVisitor>;
- * results are identical.
+ * and tiles whose neighbourhood does not fit the staging buffer, are marked VISO_PENDING and counted; the generic
+ * kernel sad_match_generic_kernel, launched right after, completes exactly those (and exits at once when there are
+ * none).
  */
 __global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, VISO_MATCH_MINB)
-sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, int reg_cap, unsigned long long* sad_pairs)
+sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, int reg_cap, unsigned long long* sad_pairs,
+                 int* n_pending)
 {
     extern __shared__ uint4 reg[];                                /* staged neighbourhood, reg_cap records */
     __shared__ WarpScratch wscr[VISO_MATCH_WARPS];
@@ -713,12 +718,9 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     const bool tile_ok = tile_s[3] >= 0;
 
     unsigned pairs = 0;
-    if (!tile_ok) {
-        for (int k = warp; k < qtot; k += VISO_MATCH_WARPS) {
-            const uint4 qrec = query_rec(k);
-            GlobalVisitor vis{job.t, g, make_geom(g, __uint_as_float(qrec.x), __uint_as_float(qrec.y), r), ws, lane, 0, true};
-            pairs += match_query(vis, job, P, ws, lane, qrec);
-        }
+    if (!tile_ok) { /* leave the whole tile to the generic kernel */
+        for (int k = threadIdx.x; k < qtot; k += blockDim.x) job.out[query_rec(k).z] = make_int4(0, 0, 0, VISO_PENDING);
+        if (threadIdx.x == 0) atomicAdd(n_pending, qtot);
     } else {
         const int R = tile_s[3];
         for (int rr = warp; rr < nrows; rr += VISO_MATCH_WARPS) {
@@ -756,9 +758,11 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
             for (int kk = warp; kk < gq; kk += VISO_MATCH_WARPS) {
                 const uint4 qrec = qrec_s[kk];
                 const int n = qcnt[kk];
-                if (n > VISO_QLIST_CAP || n > P.K) { /* top-K cut or list overflow: generic path */
-                    GlobalVisitor vis{job.t, g, make_geom(g, __uint_as_float(qrec.x), __uint_as_float(qrec.y), r), ws, lane, 0, true};
-                    pairs += match_query(vis, job, P, ws, lane, qrec);
+                if (n > VISO_QLIST_CAP || n > P.K) { /* top-K cut or list overflow: left to the generic kernel */
+                    if (lane == 0) {
+                        job.out[qrec.z] = make_int4(0, 0, 0, VISO_PENDING);
+                        atomicAdd(n_pending, 1);
+                    }
                     continue;
                 }
                 const int q = (int)qrec.z;
@@ -800,12 +804,18 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     }
 }
 
-/* variant without tile staging: CTA = VISO_STRIP_QPC consecutive cell-sorted queries, every query walks its own
- * spans in global memory (GlobalVisitor).  Selected with VISO_MATCH_MODE=strip (A/B measurements). */
-__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, VISO_MATCH_MINB)
-sad_match_strip_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, unsigned long long* sad_pairs)
+/*
+ * Generic match kernel: CTA = VISO_STRIP_QPC consecutive cell-sorted queries, one warp per query, every query walks
+ * its own grid-row spans in global memory and applies the exact top-K cut (match_query<GlobalVisitor>).  Handles any
+ * radius, max_neighbors and density.  With only_pending it completes the queries the tile kernel marked
+ * VISO_PENDING; VISO_MATCH_MODE=generic runs everything through it (A/B measurements and tests).
+ */
+__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32)
+sad_match_generic_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, unsigned long long* sad_pairs,
+                         const int* __restrict__ n_pending, int only_pending)
 {
     __shared__ WarpScratch wscr[VISO_MATCH_WARPS];
+    if (only_pending && *n_pending == 0) return;
     const MatchJob job = jobs[blockIdx.y];
     const MatchParamsDev& P = mp.p[job.mode];
     const int nq = *job.q.n, nt = *job.t.n;
@@ -815,6 +825,7 @@ sad_match_strip_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, Gr
     const int q_end = min(nq, (int)(blockIdx.x + 1) * VISO_STRIP_QPC);
     for (int qi = blockIdx.x * VISO_STRIP_QPC + warp; qi < q_end; qi += VISO_MATCH_WARPS) {
         const uint4 qrec = __ldg(job.q.srec + qi);
+        if (only_pending && job.out[qrec.z].w != VISO_PENDING) continue;
         if (nt <= 0) {
             if (lane == 0) job.out[qrec.z] = make_int4(-1, INT_MAX, INT_MAX, 0);
             continue;
@@ -1530,9 +1541,20 @@ cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStr
 }
 
 cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
-                              GridCfg g, unsigned long long* sad_pairs, cudaStream_t s)
+                              GridCfg g, unsigned long long* sad_pairs, int* n_pending, cudaStream_t s, int* launches)
 {
     if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+    static int mode = -1;
+    if (mode < 0) {
+        const char* m = getenv("VISO_MATCH_MODE");
+        mode = (m && m[0] == 'g') ? 1 : 0;
+    }
+    const dim3 ggrid((max_nq + VISO_STRIP_QPC - 1) / VISO_STRIP_QPC, n_jobs);
+    if (mode == 1) {
+        sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, n_pending, 0);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     /* staging capacity for a tile's neighbourhood: twice the expected point count of the grown tile box at the
      * densest target set, within [256, 6144] records of 16 bytes */
     const float r = fmaxf(mp.p[0].radius, mp.p[1].radius);
@@ -1545,24 +1567,19 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
     cap = (cap + 63) & ~63;
     const size_t smem = (size_t)cap * sizeof(uint4);
     static int attr_set = 0;
-    if (smem > 32 * 1024 && !attr_set) {
+    if (smem > 24 * 1024 && !attr_set) {
         cudaError_t e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 16);
         if (e != cudaSuccess) return e;
         attr_set = 1;
     }
-    static int mode = -1;
-    if (mode < 0) {
-        const char* m = getenv("VISO_MATCH_MODE");
-        mode = (m && m[0] == 's') ? 1 : 0;
-    }
-    if (mode == 1) {
-        dim3 grid((max_nq + VISO_STRIP_QPC - 1) / VISO_STRIP_QPC, n_jobs);
-        sad_match_strip_kernel<<<grid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs);
-        return cudaGetLastError();
-    }
+    cudaError_t e = cudaMemsetAsync(n_pending, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
     const int tiles = ((g.gx + VISO_TILE_W - 1) / VISO_TILE_W) * ((g.gy + VISO_TILE_H - 1) / VISO_TILE_H);
-    dim3 grid(tiles, n_jobs);
-    sad_match_kernel<<<grid, VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, sad_pairs);
+    sad_match_kernel<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, sad_pairs, n_pending);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, n_pending, 1);
+    if (launches) *launches += 2;
     return cudaGetLastError();
 }
 

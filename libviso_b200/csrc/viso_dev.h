@@ -24,13 +24,17 @@
 #ifndef VISO_MATCH_WARPS
 #define VISO_MATCH_WARPS 4
 #endif
+#ifndef VISO_EVAL_DEPTH
+#define VISO_EVAL_DEPTH 4          /* SAD steps whose row loads are issued together (4 rows each) */
+#endif
 #ifndef VISO_MATCH_MINB
-#define VISO_MATCH_MINB 5          /* resident CTAs per SM the match kernels are compiled for */
+#define VISO_MATCH_MINB 6          /* resident CTAs per SM the match kernels are compiled for */
 #endif
 #define VISO_TILE_W 6            /* query tile of sad_match: 6 x 4 cells = 96 x 64 px */
 #define VISO_TILE_H 4
 #define VISO_QLIST_CAP 128       /* per-query candidate list of the tile path (region indices) */
-#define VISO_STRIP_QPC 16         /* queries per CTA of the strip variant */
+#define VISO_STRIP_QPC 16         /* queries per CTA of the generic match kernel */
+#define VISO_PENDING (-2)         /* dense result .w: left by the tile kernel for the generic kernel */
 #define VISO_MAX_REG_ROWS 64     /* grid rows a staged tile neighbourhood may span */
 
 struct GridCfg { int gx, gy; };
@@ -141,7 +145,7 @@ struct CircleJob {             /* per frame pair */
 cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dlen, int* err_flag, cudaStream_t s);
 cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStream_t s);
 cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
-                              GridCfg g, unsigned long long* sad_pairs, cudaStream_t s);
+                              GridCfg g, unsigned long long* sad_pairs, int* n_pending, cudaStream_t s, int* launches);
 cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, int max_n, ParamDev p, cudaStream_t s);
 cudaError_t viso_launch_circle(const CircleJob* jobs, int n_jobs, cudaStream_t s);
 cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, int max_n, ParamDev p, cudaStream_t s,
