@@ -110,6 +110,10 @@ int viso_match_desc_sorted(viso_ctx* ctx, const float* kp1, int n1, const float*
                            const float* d1, const float* d2, int desc_len, const viso_match_params* params,
                            int32_t* matches, int32_t* n_matches);
 
+/* ---- std::sort(match.begin(), match.end(), by dist), reference src/viso.cpp:724: the order libstdc++'s introsort
+ * gives (the reference's sort is unstable; the order of equal distances is observable downstream).  In place. */
+int viso_sort_matches(viso_ctx* ctx, int32_t* matches, int n);
+
 /* ---- match_circle, reference src/viso.cpp:206-243.  Matches are m x 3 ints. circ4: cap nlr x 4, pcl3: cap nlr x 3 */
 int viso_match_circle(viso_ctx* ctx, const int32_t* match_lr, int nlr, const int32_t* match_lr_prev, int nlrp,
                       const int32_t* match11, int n11, const int32_t* match22, int n22,

@@ -215,6 +215,12 @@ class Context:
                                               _p(m), C.byref(nm)))
         return m[:nm.value].copy()
 
+    # ---- std::sort by dist, viso.cpp:724 ----
+    def sort_matches(self, m):
+        m = np.ascontiguousarray(_i32(m).reshape(-1, 3)).copy()
+        self._ck(lib().viso_sort_matches(self.h, _p(m), len(m)))
+        return m
+
     # ---- match_circle, viso.cpp:206-243 ----
     def match_circle(self, mlr, mlrp, m11, m22):
         mlr, mlrp, m11, m22 = (_i32(a).reshape(-1, 3) for a in (mlr, mlrp, m11, m22))

@@ -410,6 +410,49 @@ int viso_match_desc_sorted(viso_ctx* ctx, const float* kp1, int n1, const float*
                            matches, n_matches);
 }
 
+int viso_sort_matches(viso_ctx* ctx, int32_t* matches, int n)
+{
+    if (!ctx) return VISO_ERR_ARG;
+    if (n < 0 || (n > 0 && !matches)) return ctx->fail(VISO_ERR_ARG, "sort_matches: bad argument");
+    if (n == 0) return VISO_OK;
+    CK(cudaSetDevice(ctx->device));
+    /* the sort kernel consumes dense per-query results: position i plays the query index */
+    std::vector<int4> dense(n);
+    for (int i = 0; i < n; ++i) dense[i] = make_int4(matches[3 * i + 1], matches[3 * i + 2], 0, 1);
+    struct Bufs { int4* dense; int *n, *matches, *count; SortJob* job; } b;
+    auto carve = [&](Carver& c) {
+        b.dense = c.take<int4>(n); b.n = c.take<int>(1); b.matches = c.take<int>((size_t)n * 3); b.count = c.take<int>(1);
+        b.job = c.take<SortJob>(1);
+    };
+    Carver measure(nullptr);
+    carve(measure);
+    int rc = ensure_scratch(ctx, measure.off);
+    if (rc) return rc;
+    Carver real(ctx->d_scr);
+    carve(real);
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(b.dense, dense.data(), (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.n, &n, 4, cudaMemcpyHostToDevice, s));
+    SortJob sj;
+    std::memset(&sj, 0, sizeof(sj));
+    sj.dense = b.dense; sj.n = b.n; sj.matches = b.matches; sj.count = b.count; sj.stride = n;
+    CK(cudaMemcpyAsync(b.job, &sj, sizeof(sj), cudaMemcpyHostToDevice, s));
+    ParamDev pd{};
+    CK(viso_launch_sort(b.job, 1, n, pd, s));
+    ctx->launches += 1;
+    std::vector<int> out((size_t)n * 3);
+    CK(cudaMemcpyAsync(out.data(), b.matches, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<int> first(n);
+    for (int i = 0; i < n; ++i) first[i] = matches[3 * i];
+    for (int p = 0; p < n; ++p) {
+        matches[3 * p] = first[out[3 * p]];
+        matches[3 * p + 1] = out[3 * p + 1];
+        matches[3 * p + 2] = out[3 * p + 2];
+    }
+    return VISO_OK;
+}
+
 /* ------------------------------------------------------------------------------------------------ match_circle */
 
 int viso_match_circle(viso_ctx* ctx, const int32_t* match_lr, int nlr, const int32_t* match_lr_prev, int nlrp,

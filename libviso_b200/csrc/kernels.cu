@@ -842,23 +842,127 @@ sad_match_generic_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, 
 /* ------------------------------------------------------------------------------------------------ sort */
 
 /*
- * Per frame: (1) compaction of the valid dense results in query order into Match(i, best_idx, best_d1)
- * (viso.cpp:711-722), (2) the reference's std::sort order (viso.cpp:724) via the restated libstdc++ introsort
- * run by one thread, (3) pos_of_query inverse table, collect_matches (viso.cpp:501-514) and
- * triangulate_rectified<double> (viso.cpp:1146-1152).
+ * std::sort order, in parallel.  The reference sorts the Match vector with libstdc++'s UNSTABLE std::sort
+ * (viso.cpp:724); which of several equal distances comes first is a property of that algorithm, so the device
+ * reproduces the algorithm's data movement exactly instead of using its own sort (introsort.h is the sequential
+ * restatement, checked against the real std::sort on the CPU).  Two observations make it parallel:
  *
- * The sort is sequential by nature (the permutation of equal-distance matches is a property of libstdc++'s
- * algorithm), so it is made cheap instead: when the frame's matches fit the CTA's shared memory (smem_cap of
- * them, 20 bytes each) one thread sorts 8-byte (dist, position) records there -- the algorithm only looks at dist,
- * so the resulting permutation is the one std::sort gives the Match vector -- and the CTA then applies it.
- * Larger inputs are sorted in place in global memory.
+ *  (1) __unguarded_partition(first+1, last, pivot) swaps the k-th element >= pivot from the left (position L_k) with
+ *      the k-th element <= pivot from the right (position R_k) for k = 1..K, K = #{k : L_k < R_k}, and returns
+ *      cut = min(L_{K+1}, R_K): both scans only ever read positions the swaps have not touched yet, so the pairing
+ *      is a function of the ORIGINAL values.  A warp computes the two position lists with ballots, K with one
+ *      monotone predicate, and does all swaps at once.
+ *  (2) __final_insertion_sort never moves an element across the boundary of a final partition piece (everything to
+ *      the left is <=), and inside a piece it is a stable insertion sort.  So once the <=16-element pieces are known
+ *      every element computes its stable rank inside its piece, all in parallel.
+ *
+ * The median-of-3 pivot moves (3 reads, 1 swap) stay with lane 0; the depth-limit heapsort branch
+ * (__partial_sort, taken only by adversarial inputs) is run sequentially by lane 0 with the restated code.
+ * Segments are disjoint, so processing the right-hand pieces from a stack instead of by recursion does not change
+ * the result.
  */
-__global__ void __launch_bounds__(256) compact_sort_kernel(const SortJob* __restrict__ jobs, ParamDev P, int smem_cap)
+struct SortScratch {
+    int stk_first[64], stk_last[64], stk_depth[64];
+};
+
+/* partition [first+1, last) around the pivot at p[first]; returns cut.  posL / posR: scratch, last-first entries */
+__device__ __forceinline__ int warp_partition(viso_sort::KV* p, int first, int last, unsigned short* posL,
+                                              unsigned short* posR, int lane)
+{
+    const int pv = p[first].d;
+    int cl = 0, cr = 0;
+    for (int base = first + 1; base < last; base += 32) {
+        const int i = base + lane;
+        const bool in = i < last;
+        const int d = in ? p[i].d : 0;
+        const bool fL = in && !(d < pv), fR = in && !(pv < d);
+        const unsigned mL = __ballot_sync(FULL, fL), mR = __ballot_sync(FULL, fR);
+        const unsigned lt = (1u << lane) - 1;
+        if (fL) posL[cl + __popc(mL & lt)] = (unsigned short)(i - first);
+        if (fR) posR[cr + __popc(mR & lt)] = (unsigned short)(i - first);
+        cl += __popc(mL);
+        cr += __popc(mR);
+    }
+    __syncwarp();
+    /* R_k (k-th from the right) = posR[cr - k]; L_k = posL[k - 1] */
+    const int kmax = min(cl, cr);
+    int K = 0;
+    for (int k0 = 0; k0 < kmax; k0 += 32) {
+        const int k = k0 + lane;
+        const bool ok = k < kmax && posL[k] < posR[cr - 1 - k];
+        const unsigned m = __ballot_sync(FULL, ok);
+        K += __popc(m);
+        if (m != FULL) break; /* monotone: the first failure ends it */
+    }
+    for (int k = lane; k < K; k += 32) {
+        const int a = first + posL[k], b = first + posR[cr - 1 - k];
+        const viso_sort::KV t = p[a]; p[a] = p[b]; p[b] = t;
+    }
+    int cut = INT_MAX;
+    if (K < cl) cut = first + posL[K];
+    if (K > 0) cut = min(cut, first + (int)posR[cr - K]);
+    __syncwarp();
+    return cut;
+}
+
+/* __introsort_loop for p[0..n) by one warp; marks the first position of every final piece in leaf[] (pieces sorted
+ * by the heapsort branch are marked element by element: they are already in order) */
+__device__ void warp_introsort_loop(viso_sort::KV* p, int n, unsigned short* posL, unsigned short* posR,
+                                    unsigned char* leaf, SortScratch& sc, int lane)
+{
+    if (n <= 0) return;
+    int sp = 0;
+    if (lane == 0) { sc.stk_first[0] = 0; sc.stk_last[0] = n; sc.stk_depth[0] = viso_sort::lg(n) * 2; }
+    sp = 1;
+    __syncwarp();
+    while (sp > 0) {
+        --sp;
+        int first = sc.stk_first[sp], last = sc.stk_last[sp], depth = sc.stk_depth[sp];
+        __syncwarp();
+        bool heap_done = false;
+        while (last - first > 16) {
+            if (depth == 0) {
+                if (lane == 0) viso_sort::heap_sort_(p + first, last - first);
+                for (int i = first + lane; i < last; i += 32) leaf[i] = 1;
+                __syncwarp();
+                heap_done = true;
+                break;
+            }
+            --depth;
+            const int mid = first + (last - first) / 2;
+            if (lane == 0) viso_sort::median_to_first_(p, first, first + 1, mid, last - 1);
+            __syncwarp();
+            const int cut = warp_partition(p, first, last, posL + first, posR + first, lane);
+            if (lane == 0) { sc.stk_first[sp] = cut; sc.stk_last[sp] = last; sc.stk_depth[sp] = depth; }
+            ++sp;
+            __syncwarp();
+            last = cut;
+        }
+        if (!heap_done && last > first && lane == 0) leaf[first] = 1;
+    }
+    __syncwarp();
+}
+
+/*
+ * Per frame: (1) compaction of the valid dense results in query order into Match(i, best_idx, best_d1)
+ * (viso.cpp:711-722), (2) the reference's std::sort order (viso.cpp:724), (3) pos_of_query inverse table,
+ * collect_matches (viso.cpp:501-514) and triangulate_rectified<double> (viso.cpp:1146-1152).
+ *
+ * When the frame's matches fit the CTA's shared memory (smem_cap of them, 13 bytes each) 8-byte (dist, query)
+ * records are sorted there: warp 0 runs the parallel introsort loop, then every thread places one element with its
+ * stable rank inside its final piece.  The algorithm only looks at dist, so the resulting permutation is the one
+ * std::sort gives the Match vector.  Larger inputs are sorted in place in global memory by one thread with the
+ * sequential restatement.
+ */
+__global__ void __launch_bounds__(128) compact_sort_kernel(const SortJob* __restrict__ jobs, ParamDev P, int smem_cap)
 {
     extern __shared__ int sort_sm[];
     __shared__ int warp_tot[32];
-    viso_sort::KV* kv = reinterpret_cast<viso_sort::KV*>(sort_sm);          /* [smem_cap] */
-    int* stage = sort_sm + 2 * smem_cap;                                      /* [smem_cap][3] */
+    __shared__ SortScratch sc;
+    viso_sort::KV* kv = reinterpret_cast<viso_sort::KV*>(sort_sm);                    /* [smem_cap] */
+    unsigned short* posL = reinterpret_cast<unsigned short*>(sort_sm + 2 * smem_cap); /* [smem_cap] */
+    unsigned short* posR = posL + smem_cap;                                            /* [smem_cap] */
+    unsigned char* leaf = reinterpret_cast<unsigned char*>(posR + smem_cap);           /* [smem_cap] */
     const SortJob job = jobs[blockIdx.x];
     const int n = *job.n;
     int base = 0;
@@ -872,10 +976,7 @@ __global__ void __launch_bounds__(256) compact_sort_kernel(const SortJob* __rest
         const bool flag = i < n && r.w != 0;
         const int slot = block_compact_slot(flag, base, warp_tot);
         if (flag) {
-            if (slot < smem_cap) {
-                kv[slot].d = r.y; kv[slot].pos = slot;
-                stage[3 * slot + 0] = i; stage[3 * slot + 1] = r.x; stage[3 * slot + 2] = r.y;
-            }
+            if (slot < smem_cap) { kv[slot].d = r.y; kv[slot].pos = i; leaf[slot] = 0; }
             job.matches[3 * slot + 0] = i;
             job.matches[3 * slot + 1] = r.x;
             job.matches[3 * slot + 2] = r.y;
@@ -884,21 +985,37 @@ __global__ void __launch_bounds__(256) compact_sort_kernel(const SortJob* __rest
     const int M = base;
     const bool in_smem = M <= smem_cap;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (in_smem) viso_sort::sort(kv, M);
-        else viso_sort::sort(reinterpret_cast<viso_sort::M3*>(job.matches), M);
-        *job.count = M;
-    }
-    __syncthreads();
-    for (int p = threadIdx.x; p < M; p += blockDim.x) {
-        int i1, i2;
-        if (in_smem) {
-            const int src = kv[p].pos;
-            i1 = stage[3 * src]; i2 = stage[3 * src + 1];
-            job.matches[3 * p] = i1; job.matches[3 * p + 1] = i2; job.matches[3 * p + 2] = stage[3 * src + 2];
-        } else {
-            i1 = job.matches[3 * p]; i2 = job.matches[3 * p + 1];
+    if (in_smem) {
+        if (threadIdx.x < 32) {
+            if (M > 16) warp_introsort_loop(kv, M, posL, posR, leaf, sc, threadIdx.x);
+            else if (M > 0 && threadIdx.x == 0) leaf[0] = 1;
         }
+    } else if (threadIdx.x == 0) {
+        viso_sort::sort(reinterpret_cast<viso_sort::M3*>(job.matches), M);
+    }
+    if (threadIdx.x == 0) *job.count = M;
+    __syncthreads();
+    for (int e = threadIdx.x; e < M; e += blockDim.x) {
+        int p, i1, i2, d;
+        if (in_smem) {
+            /* __final_insertion_sort: stable rank inside the final piece [lo, hi) */
+            int lo = e, hi = e + 1;
+            while (!leaf[lo]) --lo;
+            while (hi < M && !leaf[hi]) ++hi;
+            const viso_sort::KV me = kv[e];
+            int rank = 0;
+            for (int j = lo; j < hi; ++j) {
+                const int dj = kv[j].d;
+                rank += (dj < me.d || (dj == me.d && j < e)) ? 1 : 0;
+            }
+            p = lo + rank;
+            i1 = me.pos; d = me.d;
+            i2 = job.dense[i1].x;
+        } else {
+            p = e;
+            i1 = job.matches[3 * p]; i2 = job.matches[3 * p + 1]; d = job.matches[3 * p + 2];
+        }
+        if (in_smem) { job.matches[3 * p] = i1; job.matches[3 * p + 1] = i2; job.matches[3 * p + 2] = d; }
         if (job.pos_of_query) job.pos_of_query[i1] = p;
         if (job.x) {
             const float2 a = job.kp1[i1], b = job.kp2[i2];
@@ -906,10 +1023,10 @@ __global__ void __launch_bounds__(256) compact_sort_kernel(const SortJob* __rest
             const int S = job.stride;
             job.x[0 * S + p] = u1; job.x[1 * S + p] = v1; job.x[2 * S + p] = u2; job.x[3 * S + p] = v2;
             if (job.X) {
-                const double d = u1 - u2;
-                job.X[0 * S + p] = P.base * (u1 - P.cu) / d;
-                job.X[1 * S + p] = P.base * (v1 - P.cv) / d;
-                job.X[2 * S + p] = P.f * P.base / d;
+                const double dd = u1 - u2;
+                job.X[0 * S + p] = P.base * (u1 - P.cu) / dd;
+                job.X[1 * S + p] = P.base * (v1 - P.cv) / dd;
+                job.X[2 * S + p] = P.f * P.base / dd;
             }
         }
     }
@@ -1586,15 +1703,16 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
 cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, int max_n, ParamDev p, cudaStream_t s)
 {
     if (n_jobs <= 0) return cudaSuccess;
-    /* 20 bytes of shared memory per match: (dist,pos) record + staged Match; up to ~200 KB per CTA */
+    /* 13 bytes of shared memory per match: (dist, query) record, two u16 position lists, piece flags */
     int cap = max_n < 1 ? 1 : max_n;
-    if (cap > 10000) cap = 10000;
-    const size_t smem = (size_t)cap * 20;
+    if (cap > 15000) cap = 15000; /* u16 positions and ~200 KB of shared memory */
+    cap = (cap + 3) & ~3;
+    const size_t smem = (size_t)cap * 13 + 16;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(compact_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    compact_sort_kernel<<<n_jobs, 256, smem, s>>>(jobs, p, cap);
+    compact_sort_kernel<<<n_jobs, 128, smem, s>>>(jobs, p, cap);
     return cudaGetLastError();
 }
 

@@ -40,6 +40,23 @@ def random_features(rng, n, w=1241, h=376, dlen=121, integer=True):
 
 # ------------------------------------------------------------------------------------------------ match_desc
 
+def test_sort_matches_is_std_sort_order(ctx, oracle):
+    """viso.cpp:724: the parallel introsort reproduces libstdc++'s permutation of equal distances (the oracle's
+    restatement is checked against the real std::sort in tests/test_oracle_golden.py)"""
+    rng = np.random.default_rng(9)
+    cases = [(0, 5), (1, 5), (2, 1), (16, 3), (17, 3), (33, 2), (700, 40), (2040, 100000), (2040, 300), (5000, 7),
+             (3000, 1), (12000, 50), (15001, 9), (40000, 2000)]
+    for n, hi in cases:
+        m = np.stack([rng.permutation(n), rng.integers(0, 10 ** 6, n), rng.integers(0, hi, n)], 1).astype(np.int32)
+        assert np.array_equal(ctx.sort_matches(m), oracle.sort_matches(m)), (n, hi)
+    # adversarial shapes: organ pipe / sorted / reverse sorted runs exercise the depth limit (heapsort branch)
+    for d in (np.r_[np.arange(3000), np.arange(3000)[::-1]], np.arange(5000), np.arange(5000)[::-1] // 3,
+              np.r_[np.arange(1, 4001, 2), np.arange(0, 4000, 2)]):
+        n = len(d)
+        m = np.stack([np.arange(n), np.arange(n)[::-1], d], 1).astype(np.int32)
+        assert np.array_equal(ctx.sort_matches(m), oracle.sort_matches(m)), n
+
+
 @pytest.mark.parametrize("mode", ["stereo", "temporal"])
 def test_match_desc_synthetic_frames(ctx, api, oracle, small_sequence, mode):
     from libviso_b200 import synth
