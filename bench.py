@@ -307,13 +307,9 @@ def main():
     tms = torch.tensor([dev_ms, e2e_ms or 0.0, float(np.mean(match_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        mine = torch.from_numpy(rec.view(np.int32).reshape(-1).copy()).cuda()
-        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, gathered, dst=0)
-        if rank == 0:
-            all_rec = [g.cpu().numpy().view(api.RECORD_DTYPE) for g in gathered]
-    else:
-        all_rec = [rec]
+    from libviso_b200.distributed import gather_records
+    got = gather_records({rank: rec}, world, F, rank, world, device="cuda")   # sequence r lives on rank r
+    all_rec = [got[s] for s in range(world)] if rank == 0 else None
     dev_ms, e2e_ms_g, mm = [float(v) for v in tms.cpu()]
 
     if rank == 0:

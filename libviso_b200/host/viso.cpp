@@ -1,0 +1,313 @@
+/*
+ * viso.cpp (B200) -- bodies of the reference's hot-path functions (see viso.h for the file:line map), each a thin
+ * marshalling layer over the C-ABI of include/viso_b200.h.  No arithmetic of the path happens here: the only host
+ * work is the std::vector / cv::Mat <-> plain-array conversion and the reference's own sampler (Algorithm S,
+ * viso.cpp:87-107) that fills the RANSAC sample table.
+ */
+#include "viso.h"
+
+#include "../../include/viso_b200.h"
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <random>
+
+namespace {
+
+struct Global {
+    std::mutex mu;
+    viso_ctx* ctx = nullptr;
+    int device = 0;
+    uint32_t seed = 424242;
+    uint64_t stream_pos = 0;          /* hypotheses drawn so far from the seed's stream */
+    vector<int> table_override;
+    ~Global() { if (ctx) viso_destroy(ctx); }
+};
+
+Global& G()
+{
+    static Global g;
+    return g;
+}
+
+viso_ctx* ctx()
+{
+    Global& g = G();
+    if (!g.ctx) {
+        const int rc = viso_create(&g.ctx, g.device);
+        if (rc != VISO_OK) throw viso_b200_error(rc, "viso_create failed: no usable CUDA device (libviso_b200 has no CPU fallback)");
+    }
+    return g.ctx;
+}
+
+void ck(int rc)
+{
+    if (rc != VISO_OK) throw viso_b200_error(rc, viso_last_error(G().ctx));
+}
+
+vector<float> kp_array(const KeyPoints& kp)
+{
+    vector<float> a(kp.size() * 2);
+    for (size_t i = 0; i < kp.size(); ++i) { a[2 * i] = kp[i].pt.x; a[2 * i + 1] = kp[i].pt.y; }
+    return a;
+}
+
+vector<int32_t> match_array(const Matches& m)
+{
+    vector<int32_t> a(m.size() * 3);
+    for (size_t i = 0; i < m.size(); ++i) { a[3 * i] = m[i][0]; a[3 * i + 1] = m[i][1]; a[3 * i + 2] = m[i][2]; }
+    return a;
+}
+
+viso_param to_c(const struct param& p)
+{
+    viso_param c;
+    std::memset(&c, 0, sizeof(c));
+    c.base = p.base; c.f = p.calib.f; c.cu = p.calib.cu; c.cv = p.calib.cv;
+    c.inlier_threshold = p.inlier_threshold; c.thresh = p.thresh; c.ransac_iter = p.ransac_iter;
+    return c;
+}
+
+/* 3 x n / 4 x n CV_64F, continuous */
+const double* mat64(const Mat& m, int rows)
+{
+    assert(m.type() == cv::DataType<double>::type && m.rows == rows && m.isContinuous());
+    (void)rows;
+    return m.ptr<double>(0);
+}
+
+} // namespace
+
+namespace viso_b200 {
+
+void set_device(int device)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    G().device = device;
+}
+
+void set_ransac_seed(uint32_t seed)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    G().seed = seed;
+    G().stream_pos = 0;
+}
+
+void set_sample_table(const vector<int>& table)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    G().table_override = table;
+}
+
+long long kernel_launches()
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    return G().ctx ? (long long)viso_launch_count(G().ctx) : 0;
+}
+
+} // namespace viso_b200
+
+/* reference src/viso.cpp:668-726 */
+void match_desc(const KeyPoints& kp1, const KeyPoints& kp2, const Descriptors& d1, const Descriptors& d2,
+                Matches& match, const MatchParams& sp)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    match.clear(); /* viso.cpp:675 */
+    assert(d1.cols == d2.cols || d1.rows == 0 || d2.rows == 0); /* BOOST_ASSERT_MSG, viso.cpp:676 */
+    assert((int)kp1.size() == d1.rows && (int)kp2.size() == d2.rows);
+    if (kp1.empty()) return;
+    viso_match_params mp;
+    std::memset(&mp, 0, sizeof(mp));
+    mp.enforce_epipolar = sp.enforce_epipolar;
+    mp.enforce_2nd_best = sp.enforce_2nd_best;
+    mp.max_neighbors = sp.max_neighbors;
+    mp.radius = sp.radius;
+    mp.sampson_thresh = sp.sampson_thresh;
+    mp.ratio_2nd_best = sp.ratio_2nd_best;
+    if (sp.enforce_epipolar) {
+        assert(sp.F.rows == 3 && sp.F.cols == 3 && sp.F.type() == cv::DataType<double>::type); /* viso.cpp:393,658 */
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) mp.F[3 * r + c] = sp.F.at<double>(r, c);
+    }
+    const vector<float> a1 = kp_array(kp1), a2 = kp_array(kp2);
+    const int dlen = d1.cols;
+    vector<int32_t> out(kp1.size() * 3);
+    int32_t n = 0;
+    ck(viso_match_desc_sorted(ctx(), a1.data(), (int)kp1.size(), a2.data(), (int)kp2.size(),
+                              d1.ptr<float>(0), kp2.empty() ? nullptr : d2.ptr<float>(0), dlen, &mp, out.data(), &n));
+    match.reserve(n);
+    for (int i = 0; i < n; ++i) match.push_back(Match(out[3 * i], out[3 * i + 1], out[3 * i + 2]));
+}
+
+/* reference src/viso.cpp:206-243 */
+void match_circle(const Matches& match_lr, const Matches& match_lr_prev, const Matches& match11,
+                  const Matches& match22, vector<Vec4i>& circ_match, Matches& match_pcl)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    const vector<int32_t> a = match_array(match_lr), b = match_array(match_lr_prev), c = match_array(match11),
+                          d = match_array(match22);
+    vector<int32_t> circ(match_lr.size() * 4 + 4), pcl(match_lr.size() * 3 + 3);
+    int32_t n = 0;
+    ck(viso_match_circle(ctx(), a.data(), (int)match_lr.size(), b.data(), (int)match_lr_prev.size(), c.data(),
+                         (int)match11.size(), d.data(), (int)match22.size(), circ.data(), pcl.data(), &n));
+    for (int i = 0; i < n; ++i) {
+        circ_match.push_back(Vec4i(circ[4 * i], circ[4 * i + 1], circ[4 * i + 2], circ[4 * i + 3])); /* :233 */
+        match_pcl.push_back(Match(pcl[3 * i], pcl[3 * i + 1], 0));                                     /* :234 */
+    }
+}
+
+/* reference src/viso.cpp:501-514 */
+void collect_matches(const KeyPoints& kp1, const KeyPoints& kp2, const Matches& match, Mat& x)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    x.create(4, (int)match.size(), cv::DataType<double>::type);
+    if (match.empty()) return;
+    const vector<float> a1 = kp_array(kp1), a2 = kp_array(kp2);
+    const vector<int32_t> m = match_array(match);
+    ck(viso_collect_triangulate(ctx(), a1.data(), (int)kp1.size(), a2.data(), (int)kp2.size(), m.data(),
+                                (int)match.size(), 0, 0, 0, 0, x.ptr<double>(0), nullptr));
+}
+
+/* reference src/viso.cpp:1137-1154 */
+template <> Mat triangulate_rectified<double>(const Mat& x, double f, double base, double c1u, double c1v)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    assert(x.type() == cv::DataType<double>::type); /* viso.cpp:1145 */
+    Mat X(3, x.cols, cv::DataType<double>::type);
+    if (x.cols > 0) ck(viso_triangulate_rectified_f64(ctx(), mat64(x, 4), x.cols, f, base, c1u, c1v, X.ptr<double>(0)));
+    return X;
+}
+
+/* reference src/viso.cpp:1509-1537.  The returned double is the reference's log-only "rms" (sqrt of the LAST
+ * point's squared error over N, :1535); it is not computed on the device and is returned as NaN. */
+pair<vector<int>, double> get_inliers(const Mat& X, const Mat& observe, vector<double>& tr, const struct param& param)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    assert(tr.size() == 6);
+    vector<int> inl(X.cols > 0 ? X.cols : 1);
+    int32_t n = 0;
+    const viso_param p = to_c(param);
+    ck(viso_get_inliers(ctx(), X.cols ? mat64(X, 3) : nullptr, X.cols ? mat64(observe, 4) : nullptr, X.cols, tr.data(),
+                        &p, inl.data(), &n));
+    inl.resize(n);
+    return std::make_pair(inl, std::nan(""));
+}
+
+/* reference src/viso.cpp:1583-1623 */
+bool minimize_reproj(const Mat& X, const Mat& observe, vector<double>& tr, const struct param& param,
+                     const vector<int>& active)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    assert(tr.size() == 6);
+    const viso_param p = to_c(param);
+    int32_t ok = 0;
+    ck(viso_minimize_reproj(ctx(), mat64(X, 3), mat64(observe, 4), X.cols, tr.data(), &p, active.data(),
+                            (int)active.size(), &ok));
+    return ok != 0;
+}
+
+/* reference src/viso.cpp:1543-1580 */
+bool ransac_minimize_reproj(const Mat& X, const Mat& observe, vector<double>& best_tr, vector<int>& best_inliers,
+                            const struct param& param)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    Global& g = G();
+    best_inliers.clear(); /* viso.cpp:1554 */
+    assert(best_tr.size() == 6);
+    const int N = X.cols, H = param.ransac_iter;
+    vector<int> table;
+    if (!g.table_override.empty()) {
+        table.swap(g.table_override);
+        if ((int)table.size() != 3 * H) throw viso_b200_error(VISO_ERR_ARG, "sample table must hold ransac_iter x 3 indices");
+    } else if (N >= 3 && H > 0) {
+        /* randomsample(3, N, sample) per hypothesis (viso.cpp:1558), drawn from ONE mt19937(seed) stream: the table
+         * for this call starts where the previous call stopped, so successive calls see fresh samples like the
+         * reference's, but reproducibly */
+        vector<int> all((size_t)3 * (g.stream_pos + H));
+        viso_randomsample_table(g.seed, (int)(g.stream_pos + H), N, all.data());
+        table.assign(all.begin() + 3 * g.stream_pos, all.end());
+        g.stream_pos += H;
+    }
+    const viso_param p = to_c(param);
+    vector<int> inl(N > 0 ? N : 1);
+    int32_t n_inl = 0, ok = 0;
+    ck(viso_ransac_minimize_reproj(ctx(), N ? mat64(X, 3) : nullptr, N ? mat64(observe, 4) : nullptr, N, &p,
+                                   table.empty() ? nullptr : table.data(), best_tr.data(), inl.data(), &n_inl, &ok,
+                                   nullptr, nullptr, nullptr, nullptr));
+    best_inliers.assign(inl.begin(), inl.begin() + n_inl);
+    return ok != 0;
+}
+
+/* reference src/viso.cpp:109-133 */
+void tr2mat(vector<double> tr, Mat& Tr)
+{
+    assert(tr.size() == 6);
+    Tr.create(4, 4, cv::DataType<double>::type);
+    viso_tr2mat(tr.data(), Tr.ptr<double>(0));
+}
+
+/* reference src/mvg.h:41-66 (T = double), without the normalisation of viso.cpp:1177-1180 */
+Mat F_from_P(const Mat& P1, const Mat& P2)
+{
+    assert(P1.rows == 3 && P1.cols == 4 && P2.rows == 3 && P2.cols == 4);
+    Mat F(3, 3, cv::DataType<double>::type);
+    viso_F_from_P(P1.ptr<double>(0), P2.ptr<double>(0), 0, F.ptr<double>(0));
+    return F;
+}
+
+/* the per-frame loop of reference src/viso.cpp:1167-1330, batched */
+vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, FeatureSequence& frames)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    Global& g = G();
+    vector<Mat> poses;
+    poses.push_back(Mat::eye(4, 4, cv::DataType<double>::type)); /* viso.cpp:1189-1190 */
+    const int F = (int)frames.size();
+    if (F == 0) return poses;
+    int cap = 1, dlen = 0;
+    for (int t = 0; t < F; ++t) {
+        const FrameFeatures& f = frames.frame(t);
+        cap = std::max(cap, (int)std::max(f.kp1.size(), f.kp2.size()));
+        if (f.d1.rows > 0) dlen = f.d1.cols;
+    }
+    if (dlen == 0) return poses;
+    struct param prm; /* viso.cpp:1182: defaults; base / calib are derived from P1, P2 by viso_seq_set_calib */
+    prm.base = 0; prm.calib.f = 0; prm.calib.cu = 0; prm.calib.cv = 0;
+    viso_seq* seq = nullptr;
+    ck(viso_seq_create(ctx(), F, cap, dlen, prm.ransac_iter, &seq));
+    try {
+        ck(viso_seq_set_calib(seq, p1.ptr<double>(0), p2.ptr<double>(0)));
+        for (int t = 0; t < F; ++t) {
+            const FrameFeatures& f = frames.frame(t);
+            const vector<float> a1 = kp_array(f.kp1), a2 = kp_array(f.kp2);
+            ck(viso_seq_upload_frame(seq, t, a1.data(), (int)f.kp1.size(), a2.data(), (int)f.kp2.size(),
+                                     f.kp1.empty() ? nullptr : f.d1.ptr<float>(0),
+                                     f.kp2.empty() ? nullptr : f.d2.ptr<float>(0)));
+            ck(viso_sync(ctx())); /* a1 / a2 are pageable temporaries */
+        }
+        /* sample seeds for every (frame pair, hypothesis): one mt19937(seed) stream */
+        vector<uint32_t> seeds((size_t)F * prm.ransac_iter * 3);
+        {
+            std::mt19937 gen(g.seed);
+            for (auto& s : seeds) s = (uint32_t)gen();
+        }
+        viso_param p = to_c(prm);
+        ck(viso_seq_run(seq, &p, seeds.data()));
+        vector<viso_record> rec(F);
+        ck(viso_seq_download(seq, rec.data()));
+        vector<double> chained((size_t)F * 16);
+        const int np = viso_chain_poses(rec.data(), F, chained.data()); /* viso.cpp:1313-1321 */
+        for (int i = 1; i < np; ++i) {
+            Mat pose(4, 4, cv::DataType<double>::type);
+            std::memcpy(pose.ptr<double>(0), &chained[(size_t)16 * i], 16 * sizeof(double));
+            poses.push_back(pose);
+        }
+    } catch (...) {
+        viso_seq_destroy(seq);
+        throw;
+    }
+    viso_seq_destroy(seq);
+    return poses;
+}
