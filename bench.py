@@ -46,6 +46,10 @@ def parse_args():
                     help="distinct rendered frames; the sequence drives back and forth over them (every frame has "
                          "its own HBM copy, so the working set is the full --frames)")
     ap.add_argument("--cpu-pairs", type=int, default=96, help="frame pairs in the cpu_baseline sample")
+    ap.add_argument("--chunk", type=int, default=200, help="frames per upload/compute chunk of the e2e pipeline")
+    ap.add_argument("--input", default="images", choices=["images", "descriptors"],
+                    help="what crosses the boundary per frame: the two 8-bit images + keypoints (descriptors extracted "
+                         "on the device, viso.cpp:1004-1024) or the reference's n x 121 f32 descriptor matrices")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -195,6 +199,9 @@ def workload_config(args):
             "frames": args.frames, "features": args.features, "ransac_iter": args.hyp,
             "unique_rendered_frames": min(args.unique, args.frames),
             "l2": "inputs larger than L2 (every frame has its own HBM copy: ~3 GB per sequence vs 126 MB L2)",
+            "input": ("two 8-bit images + keypoints per frame, descriptors extracted on the device (viso.cpp:1004-1024)"
+                      if args.input == "images" else "keypoints + n x 121 f32 descriptor matrices per frame (cv::Mat layout)"),
+            "e2e_pipeline": f"chunks of {args.chunk} frames: H2D on a copy stream overlapped with the previous chunk's kernels",
             "parallelism": f"{args.gpus} independent sequence(s), one per GPU, NCCL gather of 64-byte records"}
 
 
@@ -216,6 +223,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -237,24 +246,37 @@ def main():
     param = api.param_default(ransac_iter=H)
 
     # pinned host copies of the unique frames (the e2e path uploads from these every step)
+    use_img = args.input == "images"
+    if use_img:
+        seq.set_image_size(synth.W, synth.H)
     pinned = []
     for f in frames:
         p = {}
-        for k in ("kpL", "kpR", "dL", "dR"):
-            tns = torch.from_numpy(np.ascontiguousarray(f[k], dtype=np.float32)).pin_memory()
-            p[k] = tns
+        for k in ("kpL", "kpR") + (("imL", "imR") if use_img else ("dL", "dR")):
+            dt = np.uint8 if k.startswith("im") else np.float32
+            p[k] = torch.from_numpy(np.ascontiguousarray(f[k], dtype=dt)).pin_memory()
         p["nL"], p["nR"] = len(f["kpL"]), len(f["kpR"])
         pinned.append(p)
     seeds_pin = torch.from_numpy(seeds.view(np.int32)).pin_memory()
     rec_pin = torch.zeros(F * 16, dtype=torch.int32).pin_memory()
 
-    def upload_all():
-        for t in range(F):
+    def upload_range(t0, t1):
+        for t in range(t0, t1):
             p = pinned[order[t]]
-            seq.upload_frame_raw(t, p["kpL"].data_ptr(), p["nL"], p["kpR"].data_ptr(), p["nR"],
-                                 p["dL"].data_ptr(), p["dR"].data_ptr())
+            if use_img:
+                seq.upload_frame_images_raw(t, p["imL"].data_ptr(), p["imR"].data_ptr(), p["kpL"].data_ptr(), p["nL"],
+                                            p["kpR"].data_ptr(), p["nR"])
+            else:
+                seq.upload_frame_raw(t, p["kpL"].data_ptr(), p["nL"], p["kpR"].data_ptr(), p["nR"],
+                                     p["dL"].data_ptr(), p["dR"].data_ptr())
 
-    h2d = sum((pinned[i]["nL"] + pinned[i]["nR"]) * (8 + 121 * 4) for i in order) + seeds.nbytes
+    def upload_all():
+        upload_range(0, F)
+
+    if use_img:  # keypoint rows are uploaded padded to the sequence capacity
+        h2d = F * (2 * synth.W * synth.H + 2 * seq.capacity() * 8) + seeds.nbytes
+    else:
+        h2d = sum((pinned[i]["nL"] + pinned[i]["nR"]) * (8 + 121 * 4) for i in order) + seeds.nbytes
     d2h = F * 64
     n_pairs = F - 1
 
@@ -284,10 +306,33 @@ def main():
     # ---- end to end through the C-ABI with host buffers ----
     e2e_ms = None
     if not args.no_e2e:
+        if use_img:
+            # the sequence as a camera / front-end would leave it in pinned host memory: per frame the two images back
+            # to back, keypoints padded to the sequence capacity -- so a chunk of frames is three large copies
+            capq = seq.capacity()
+            img_host = torch.empty((F, 2, synth.H, synth.W), dtype=torch.uint8).pin_memory()
+            kpL_host = torch.zeros((F, capq, 2), dtype=torch.float32).pin_memory()
+            kpR_host = torch.zeros((F, capq, 2), dtype=torch.float32).pin_memory()
+            nL_host = torch.zeros(F, dtype=torch.int32); nR_host = torch.zeros(F, dtype=torch.int32)
+            for t in range(F):
+                p = pinned[order[t]]
+                img_host[t, 0] = p["imL"]; img_host[t, 1] = p["imR"]
+                kpL_host[t, :p["nL"]] = p["kpL"]; kpR_host[t, :p["nR"]] = p["kpR"]
+                nL_host[t] = p["nL"]; nR_host[t] = p["nR"]
+            img_b, kp_b = 2 * synth.H * synth.W, capq * 8
+
         def e2e_step():
-            upload_all()
+            # chunked pipeline: the uploads of chunk k+1 (copy stream) overlap the kernels of chunk k
             ctx._ck(api.lib().viso_seq_set_seeds(seq.h, api._p(seeds_pin.data_ptr()), H))
-            seq.run(param)
+            for t0 in range(0, F, args.chunk):
+                t1 = min(F, t0 + args.chunk)
+                if use_img:
+                    seq.upload_chunk_images_raw(t0, t1 - t0, img_host.data_ptr() + t0 * img_b, kpL_host.data_ptr() + t0 * kp_b,
+                                                nL_host.data_ptr() + 4 * t0, kpR_host.data_ptr() + t0 * kp_b,
+                                                nR_host.data_ptr() + 4 * t0)
+                else:
+                    upload_range(t0, t1)
+                seq.run_range(param, t0, t1)
             seq.download_raw(rec_pin.data_ptr())
         for _ in range(2):
             e2e_step()

@@ -168,6 +168,24 @@ int viso_seq_set_calib(viso_seq* seq, const double P1[12], const double P2[12]);
 /* host -> device copy of one frame's features (through pinned staging, asynchronous on the context stream) */
 int viso_seq_upload_frame(viso_seq* seq, int t, const float* kpL, int nL, const float* kpR, int nR,
                           const float* dL, const float* dR);
+/* Front-end on the device: MyFeatureExtractor::computeImpl, reference src/viso.cpp:1004-1024 (cv::Sobel x 3x3,
+ * BORDER_REFLECT_101, 11x11 patch around Point2i(kp.pt), samples with row/col <= 0 or >= size are 0).  Instead of
+ * the n x 121 f32 descriptor matrix (484 B per keypoint) the caller uploads the two 8-bit images of the frame
+ * (width*height bytes each, rows contiguous) and the keypoints; the descriptors are computed on the device straight
+ * into the packed layout.  Results are identical to uploading the reference's descriptors.  desc_len must be 121. */
+int viso_seq_set_image_size(viso_seq* seq, int width, int height);
+int viso_seq_upload_frame_images(viso_seq* seq, int t, const uint8_t* imgL, const uint8_t* imgR,
+                                 const float* kpL, int nL, const float* kpR, int nR);
+/* The same for `count` consecutive frames in three copies (large copies reach PCIe peak, per-frame ones do not):
+ * images = count x [left, right] x height x width bytes; kpL / kpR = count x viso_seq_capacity() x 2 floats (row i
+ * holds nL[i] / nR[i] keypoints, the rest is ignored). */
+int viso_seq_capacity(const viso_seq* seq);
+int viso_seq_upload_chunk_images(viso_seq* seq, int t0, int count, const uint8_t* images, const float* kpL,
+                                 const int32_t* nL, const float* kpR, const int32_t* nR);
+/* Uploads run on a dedicated copy stream.  viso_seq_run_range() orders itself after every upload enqueued so far and
+ * enqueues the pipeline for frames [t0, t1) (frame pairs (t-1, t) for t in [max(t0,1), t1); frame t0-1 must have been
+ * run before), so uploading chunk k+1 from pinned memory overlaps the kernels of chunk k. */
+int viso_seq_run_range(viso_seq* seq, const viso_param* param, int t0, int t1);
 /* enqueue the whole pipeline for frames [0, n_frames).  seeds: host [n_frames][ransac_iter][3] uint32 (copied). */
 int viso_seq_run(viso_seq* seq, const viso_param* param, const uint32_t* seeds);
 /* same but the seeds are already on the device from a previous viso_seq_run / viso_seq_set_seeds */
@@ -185,6 +203,8 @@ int viso_seq_stats(viso_seq* seq, int64_t* match_bytes, int64_t* sad_pairs, int6
 int viso_seq_match_ms(viso_seq* seq, float* ms);
 /* parity-test getters (host copies).  which: 0 = stereo (frame t), 1 = temporal left (t vs t-1), 2 = temporal right */
 int viso_seq_get_dense(viso_seq* seq, int which, int t, int32_t* out4 /* n x 4: idx,d1,d2,valid */, int32_t* n);
+/* packed descriptor rows (n x 128 u16, value + 1024, pad 0) of frame t; side 0 = left, 1 = right */
+int viso_seq_get_packed(viso_seq* seq, int t, int side, uint16_t* rows, int32_t* n);
 int viso_seq_get_lr_matches(viso_seq* seq, int t, int32_t* matches3, int32_t* n);
 int viso_seq_get_circ(viso_seq* seq, int t, int32_t* circ4, int32_t* pcl2, int32_t* n);
 int viso_seq_get_inliers(viso_seq* seq, int t, int32_t* inliers, int32_t* n);

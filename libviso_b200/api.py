@@ -322,6 +322,7 @@ class Sequence:
     def upload_frame(self, t, kpL, kpR, dL, dR):
         kpL, kpR, dL, dR = _f32(kpL).reshape(-1, 2), _f32(kpR).reshape(-1, 2), _f32(dL), _f32(dR)
         self.ctx._ck(lib().viso_seq_upload_frame(self.h, t, _p(kpL), len(kpL), _p(kpR), len(kpR), _p(dL), _p(dR)))
+        self.ctx.sync()  # the numpy temporaries are pageable and may die
 
     def upload_frame_raw(self, t, kpL_ptr, nL, kpR_ptr, nR, dL_ptr, dR_ptr):
         """same with raw host addresses (pinned buffers): the copies are then truly asynchronous"""
@@ -330,6 +331,39 @@ class Sequence:
     def upload(self, frames):
         for t, f in enumerate(frames):
             self.upload_frame(t, f["kpL"], f["kpR"], f["dL"], f["dR"])
+
+    # ---- device front-end: MyFeatureExtractor (viso.cpp:1004-1024) from the 8-bit images ----
+    def set_image_size(self, width, height):
+        self.ctx._ck(lib().viso_seq_set_image_size(self.h, int(width), int(height)))
+
+    def upload_frame_images(self, t, imL, imR, kpL, kpR):
+        imL, imR = np.ascontiguousarray(imL, dtype=np.uint8), np.ascontiguousarray(imR, dtype=np.uint8)
+        kpL, kpR = _f32(kpL).reshape(-1, 2), _f32(kpR).reshape(-1, 2)
+        self.ctx._ck(lib().viso_seq_upload_frame_images(self.h, t, _p(imL), _p(imR), _p(kpL), len(kpL), _p(kpR), len(kpR)))
+        self.ctx.sync()  # the numpy temporaries are pageable and may die
+
+    def upload_frame_images_raw(self, t, imL_ptr, imR_ptr, kpL_ptr, nL, kpR_ptr, nR):
+        self.ctx._ck(lib().viso_seq_upload_frame_images(self.h, t, _p(imL_ptr), _p(imR_ptr), _p(kpL_ptr), nL, _p(kpR_ptr), nR))
+
+    def capacity(self):
+        return int(lib().viso_seq_capacity(self.h))
+
+    def upload_chunk_images_raw(self, t0, count, images_ptr, kpL_ptr, nL_ptr, kpR_ptr, nR_ptr):
+        """count frames in three copies from (pinned) host blocks: images [count][2][H][W] u8, kp [count][capacity()][2] f32"""
+        self.ctx._ck(lib().viso_seq_upload_chunk_images(self.h, int(t0), int(count), _p(images_ptr), _p(kpL_ptr), _p(nL_ptr),
+                                                        _p(kpR_ptr), _p(nR_ptr)))
+
+    def upload_images(self, frames):
+        for t, f in enumerate(frames):
+            self.upload_frame_images(t, f["imL"], f["imR"], f["kpL"], f["kpR"])
+
+    def run_range(self, param, t0, t1):
+        self.ctx._ck(lib().viso_seq_run_range(self.h, C.byref(param), int(t0), int(t1)))
+
+    def get_packed(self, t, side):
+        out = np.zeros((self.max_kp + 32, 128), np.uint16); n = C.c_int32(0)
+        self.ctx._ck(lib().viso_seq_get_packed(self.h, t, side, _p(out), C.byref(n)))
+        return out[:n.value].copy()
 
     def set_seeds(self, seeds, ransac_iter):
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32)

@@ -30,6 +30,7 @@ struct viso_ctx {
     char* d_scr = nullptr;
     size_t d_cap = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaStream_t copy_stream = nullptr;   /* host -> device uploads of sequence objects (overlap with compute) */
 
     int fail(int code, const std::string& msg)
     {
@@ -180,6 +181,11 @@ int viso_create(viso_ctx** out, int device)
         delete ctx;
         return VISO_ERR_CUDA;
     }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return VISO_ERR_CUDA;
+    }
     *out = ctx;
     return VISO_OK;
 }
@@ -192,6 +198,8 @@ void viso_destroy(viso_ctx* ctx)
     if (ctx->d_scr) cudaFree(ctx->d_scr);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -202,6 +210,7 @@ void* viso_stream(viso_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int viso_sync(viso_ctx* ctx)
 {
     if (!ctx) return VISO_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return VISO_OK;
 }
@@ -339,7 +348,7 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
         CK(cudaMemcpyAsync(b.xy2, kp2, (size_t)n2 * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(b.df2, d2, (size_t)n2 * dlen * 4, cudaMemcpyHostToDevice, s));
     }
-    PackJob pj[2] = {{b.df1, b.counts, b.du1, b.rs1}, {b.df2, b.counts + 1, b.du2, b.rs2}};
+    PackJob pj[2] = {{b.df1, b.counts, b.du1, b.rs1, nullptr}, {b.df2, b.counts + 1, b.du2, b.rs2, nullptr}};
     GridJob gj[2] = {{b.xy1, b.counts, b.rs1, b.srec1, b.cell1}, {b.xy2, b.counts + 1, b.rs2, b.srec2, b.cell2}};
     MatchJob mj;
     mj.q = SetView{b.xy1, b.counts, b.du1, b.srec1, b.cell1};
@@ -919,7 +928,13 @@ struct viso_seq {
     unsigned long long* pairs = nullptr;
     int* err = nullptr;
     int* pending = nullptr;
-    std::vector<int> h_nL, h_nR;
+    int *h_nL = nullptr, *h_nR = nullptr, *h_from_image = nullptr; /* pinned: truly asynchronous count uploads */
+    int* from_image = nullptr;            /* device [F]: frame t's descriptors come from its images */
+    unsigned char *imgL = nullptr, *imgR = nullptr;
+    int img_w = 0, img_h = 0;
+    ExtractJob* extract_jobs = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
+    int run_hi = 0;                       /* frames [0, run_hi) may still be read by enqueued kernels */
     std::vector<RansacProb> h_probs;
     int H_cur = -1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -945,6 +960,9 @@ void seq_free(viso_seq* s)
     for (void* p : s->allocs) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_copy) cudaEventDestroy(s->ev_copy);
+    if (s->ev_compute) cudaEventDestroy(s->ev_compute);
+    if (s->h_nL) cudaFreeHost(s->h_nL);
     delete s;
 }
 
@@ -986,15 +1004,23 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     SA(hyp_ok, F * H); SA(hyp_count, F * H); SA(inliers, F * cap); SA(active, F * cap);
     SA(rec, F); SA(seeds, F * H * 3);
     SA(pack_jobs, 2 * F); SA(grid_jobs, 2 * F); SA(match_jobs, 3 * F); SA(sort_jobs, F); SA(circ_jobs, F); SA(probs, F);
-    SA(pairs, 2); SA(err, 1); SA(pending, 1);
+    SA(pairs, 2); SA(err, 1); SA(pending, 1); SA(from_image, F); SA(extract_jobs, 2 * F);
 #undef SA
-    s->h_nL.assign(F, 0);
-    s->h_nR.assign(F, 0);
+    if (cudaMallocHost(&s->h_nL, 3 * F * sizeof(int)) != cudaSuccess) {
+        seq_free(s);
+        return ctx->fail(VISO_ERR_NOMEM, "seq_create: cudaMallocHost failed");
+    }
+    s->h_nR = s->h_nL + F;
+    s->h_from_image = s->h_nL + 2 * F;
+    std::memset(s->h_nL, 0, 3 * F * sizeof(int));
     cudaStream_t st = ctx->stream;
     auto bail = [&](cudaError_t e, const char* what) { seq_free(s); return ctx->fail_cuda(e, what); };
     cudaError_t e;
     if ((e = cudaEventCreate(&s->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&s->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&s->ev_compute, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMemsetAsync(s->from_image, 0, F * 4, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
     if ((e = cudaMemsetAsync(s->nL, 0, F * 4, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
     if ((e = cudaMemsetAsync(s->nR, 0, F * 4, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
     if ((e = cudaMemsetAsync(s->lr_count, 0, F * 4, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
@@ -1019,8 +1045,10 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
                        s->cellR + t * nc};
     };
     for (size_t t = 0; t < F; ++t) {
-        pj[2 * t] = PackJob{s->dLf + t * cap * desc_len, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->rsL + t * cap};
-        pj[2 * t + 1] = PackJob{s->dRf + t * cap * desc_len, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->rsR + t * cap};
+        pj[2 * t] = PackJob{s->dLf + t * cap * desc_len, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->rsL + t * cap,
+                            s->from_image + t};
+        pj[2 * t + 1] = PackJob{s->dRf + t * cap * desc_len, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->rsR + t * cap,
+                                s->from_image + t};
         gj[2 * t] = GridJob{s->kpL + t * cap, s->nL + t, s->rsL + t * cap, s->srecL + t * cap, s->cellL + t * nc};
         gj[2 * t + 1] = GridJob{s->kpR + t * cap, s->nR + t, s->rsR + t * cap, s->srecR + t * cap, s->cellR + t * nc};
         MatchJob m;
@@ -1083,6 +1111,18 @@ int viso_seq_set_calib(viso_seq* s, const double P1[12], const double P2[12])
     return VISO_OK;
 }
 
+/* an upload that overwrites a frame enqueued kernels may still read has to wait for them (not for the others: that
+ * is what lets the uploads of one chunk overlap the kernels of the previous one) */
+static int upload_guard(viso_seq* s, int t)
+{
+    viso_ctx* ctx = s->ctx;
+    if (t < s->run_hi) {
+        CK(cudaStreamWaitEvent(ctx->copy_stream, s->ev_compute, 0));
+        s->run_hi = 0; /* everything enqueued so far is now ordered before later uploads */
+    }
+    return VISO_OK;
+}
+
 int viso_seq_upload_frame(viso_seq* s, int t, const float* kpL, int nL, const float* kpR, int nR, const float* dL,
                           const float* dR)
 {
@@ -1091,7 +1131,9 @@ int viso_seq_upload_frame(viso_seq* s, int t, const float* kpL, int nL, const fl
     if (t < 0 || t >= s->F || nL < 0 || nR < 0 || nL > s->cap || nR > s->cap) return ctx->fail(VISO_ERR_ARG, "seq_upload_frame: bad frame index or keypoint count");
     if ((nL > 0 && (!kpL || !dL)) || (nR > 0 && (!kpR || !dR))) return ctx->fail(VISO_ERR_ARG, "seq_upload_frame: null input");
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+    int rc = upload_guard(s, t);
+    if (rc) return rc;
+    cudaStream_t st = ctx->copy_stream;
     const size_t cap = s->cap, dl = s->dlen;
     if (nL > 0) {
         CK(cudaMemcpyAsync(s->kpL + t * cap, kpL, (size_t)nL * 8, cudaMemcpyHostToDevice, st));
@@ -1103,6 +1145,91 @@ int viso_seq_upload_frame(viso_seq* s, int t, const float* kpL, int nL, const fl
     }
     s->h_nL[t] = nL;
     s->h_nR[t] = nR;
+    s->h_from_image[t] = 0;
+    return VISO_OK;
+}
+
+int viso_seq_set_image_size(viso_seq* s, int width, int height)
+{
+    if (!s) return VISO_ERR_ARG;
+    viso_ctx* ctx = s->ctx;
+    if (width < 3 || height < 3) return ctx->fail(VISO_ERR_ARG, "seq_set_image_size: images must be at least 3 x 3");
+    if (s->dlen != 121) return ctx->fail(VISO_ERR_DOMAIN, "seq_set_image_size: the device extractor produces 11 x 11 descriptors (desc_len 121)");
+    if (s->imgL) return (width == s->img_w && height == s->img_h) ? VISO_OK : ctx->fail(VISO_ERR_ARG, "seq_set_image_size: size already set");
+    CK(cudaSetDevice(ctx->device));
+    const size_t F = s->F, cap = s->cap, bytes = (size_t)width * height;
+    cudaError_t e;
+    /* one allocation, [frame][left, right][height][width]: a run of frames is one contiguous block */
+    if ((e = seq_alloc(s, &s->imgL, 2 * F * bytes)) != cudaSuccess) {
+        ctx->err = std::string("seq_set_image_size cudaMalloc: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? VISO_ERR_NOMEM : VISO_ERR_CUDA;
+    }
+    s->imgR = s->imgL + bytes;
+    s->img_w = width; s->img_h = height;
+    std::vector<ExtractJob> ej(2 * F);
+    for (size_t t = 0; t < F; ++t) {
+        ej[2 * t] = ExtractJob{s->imgL + 2 * t * bytes, s->kpL + t * cap, s->nL + t, s->dLu + t * cap * VISO_DESC_U16,
+                               s->rsL + t * cap, s->from_image + t};
+        ej[2 * t + 1] = ExtractJob{s->imgR + 2 * t * bytes, s->kpR + t * cap, s->nR + t, s->dRu + t * cap * VISO_DESC_U16,
+                                   s->rsR + t * cap, s->from_image + t};
+    }
+    CK(cudaMemcpyAsync(s->extract_jobs, ej.data(), ej.size() * sizeof(ExtractJob), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VISO_OK;
+}
+
+int viso_seq_upload_frame_images(viso_seq* s, int t, const uint8_t* imgL, const uint8_t* imgR, const float* kpL, int nL,
+                                 const float* kpR, int nR)
+{
+    if (!s) return VISO_ERR_ARG;
+    viso_ctx* ctx = s->ctx;
+    if (!s->imgL) return ctx->fail(VISO_ERR_ARG, "seq_upload_frame_images: viso_seq_set_image_size has not been called");
+    if (t < 0 || t >= s->F || nL < 0 || nR < 0 || nL > s->cap || nR > s->cap) return ctx->fail(VISO_ERR_ARG, "seq_upload_frame_images: bad frame index or keypoint count");
+    if (!imgL || !imgR || (nL > 0 && !kpL) || (nR > 0 && !kpR)) return ctx->fail(VISO_ERR_ARG, "seq_upload_frame_images: null input");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_guard(s, t);
+    if (rc) return rc;
+    cudaStream_t st = ctx->copy_stream;
+    const size_t cap = s->cap, bytes = (size_t)s->img_w * s->img_h;
+    if (imgR == imgL + bytes) {
+        CK(cudaMemcpyAsync(s->imgL + 2 * t * bytes, imgL, 2 * bytes, cudaMemcpyHostToDevice, st));
+    } else {
+        CK(cudaMemcpyAsync(s->imgL + 2 * t * bytes, imgL, bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s->imgR + 2 * t * bytes, imgR, bytes, cudaMemcpyHostToDevice, st));
+    }
+    if (nL > 0) CK(cudaMemcpyAsync(s->kpL + t * cap, kpL, (size_t)nL * 8, cudaMemcpyHostToDevice, st));
+    if (nR > 0) CK(cudaMemcpyAsync(s->kpR + t * cap, kpR, (size_t)nR * 8, cudaMemcpyHostToDevice, st));
+    s->h_nL[t] = nL;
+    s->h_nR[t] = nR;
+    s->h_from_image[t] = 1;
+    return VISO_OK;
+}
+
+int viso_seq_capacity(const viso_seq* s) { return s ? s->cap : 0; }
+
+int viso_seq_upload_chunk_images(viso_seq* s, int t0, int count, const uint8_t* images, const float* kpL, const int32_t* nL,
+                                 const float* kpR, const int32_t* nR)
+{
+    if (!s) return VISO_ERR_ARG;
+    viso_ctx* ctx = s->ctx;
+    if (!s->imgL) return ctx->fail(VISO_ERR_ARG, "seq_upload_chunk_images: viso_seq_set_image_size has not been called");
+    if (t0 < 0 || count < 1 || t0 + count > s->F || !images || !kpL || !kpR || !nL || !nR)
+        return ctx->fail(VISO_ERR_ARG, "seq_upload_chunk_images: bad argument");
+    for (int i = 0; i < count; ++i)
+        if (nL[i] < 0 || nR[i] < 0 || nL[i] > s->cap || nR[i] > s->cap) return ctx->fail(VISO_ERR_ARG, "seq_upload_chunk_images: bad keypoint count");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_guard(s, t0);
+    if (rc) return rc;
+    cudaStream_t st = ctx->copy_stream;
+    const size_t cap = s->cap, bytes = (size_t)s->img_w * s->img_h;
+    CK(cudaMemcpyAsync(s->imgL + 2 * (size_t)t0 * bytes, images, 2 * (size_t)count * bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->kpL + (size_t)t0 * cap, kpL, (size_t)count * cap * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->kpR + (size_t)t0 * cap, kpR, (size_t)count * cap * 8, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < count; ++i) {
+        s->h_nL[t0 + i] = nL[i];
+        s->h_nR[t0 + i] = nR[i];
+        s->h_from_image[t0 + i] = 1;
+    }
     return VISO_OK;
 }
 
@@ -1112,7 +1239,9 @@ int viso_seq_set_seeds(viso_seq* s, const uint32_t* seeds, int ransac_iter)
     viso_ctx* ctx = s->ctx;
     if (ransac_iter < 0 || ransac_iter > s->maxH || (ransac_iter > 0 && !seeds)) return ctx->fail(VISO_ERR_ARG, "seq_set_seeds: bad argument");
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+    int rc = upload_guard(s, 0);
+    if (rc) return rc;
+    cudaStream_t st = ctx->copy_stream;
     const size_t H = ransac_iter;
     if (H > 0) CK(cudaMemcpyAsync(s->seeds, seeds, (size_t)s->F * H * 12, cudaMemcpyHostToDevice, st));
     if (s->H_cur != ransac_iter) {
@@ -1128,25 +1257,35 @@ int viso_seq_set_seeds(viso_seq* s, const uint32_t* seeds, int ransac_iter)
     return VISO_OK;
 }
 
-int viso_seq_run_resident(viso_seq* s, const viso_param* param)
+int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
 {
     if (!s) return VISO_ERR_ARG;
     viso_ctx* ctx = s->ctx;
     if (!param) return ctx->fail(VISO_ERR_ARG, "seq_run: null param");
+    if (t0 < 0 || t1 > s->F || t0 >= t1) return ctx->fail(VISO_ERR_ARG, "seq_run_range: bad frame range");
     if (!s->calib_set) return ctx->fail(VISO_ERR_ARG, "seq_run: viso_seq_set_calib has not been called");
     if (s->H_cur != param->ransac_iter) return ctx->fail(VISO_ERR_ARG, "seq_run: seeds were set for a different ransac_iter");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const int F = s->F;
-    CK(cudaMemcpyAsync(s->nL, s->h_nL.data(), (size_t)F * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->nR, s->h_nR.data(), (size_t)F * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(s->pairs, 0, 16, st));
-    CK(cudaMemsetAsync(s->err, 0, 4, st));
-    int max_n = 0, max_nL = 0;
-    for (int t = 0; t < F; ++t) {
+    /* everything uploaded so far (frames, seeds) is visible to the kernels below */
+    CK(cudaEventRecord(s->ev_copy, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(st, s->ev_copy, 0));
+    const int nf = t1 - t0;
+    CK(cudaMemcpyAsync(s->nL + t0, s->h_nL + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->nR + t0, s->h_nR + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->from_image + t0, s->h_from_image + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    if (t0 == 0) {
+        CK(cudaMemsetAsync(s->pairs, 0, 16, st));
+        CK(cudaMemsetAsync(s->err, 0, 4, st));
+    }
+    int max_n = 0, max_nL = 0, any_img = 0, any_f32 = 0;
+    for (int t = t0; t < t1; ++t) {
         max_n = std::max(max_n, std::max(s->h_nL[t], s->h_nR[t]));
         max_nL = std::max(max_nL, s->h_nL[t]);
+        if (s->h_from_image[t]) any_img = 1; else any_f32 = 1;
     }
+    int max_nt = max_n; /* the temporal targets of frame t0 live in frame t0 - 1 */
+    if (t0 > 0) max_nt = std::max(max_nt, std::max(s->h_nL[t0 - 1], s->h_nR[t0 - 1]));
     viso_param pp = *param;
     pp.base = s->base; pp.f = s->f; pp.cu = s->cu; pp.cv = s->cv;
     const ParamDev pd = make_param_dev(&pp);
@@ -1157,24 +1296,39 @@ int viso_seq_run_resident(viso_seq* s, const viso_param* param)
     mp.p[0] = make_match_dev(&ms);
     mp.p[1] = make_match_dev(&mt);
 
-    CK(viso_launch_pack(s->pack_jobs, 2 * F, max_n, s->dlen, s->err, st));
-    CK(viso_launch_grid(s->grid_jobs, 2 * F, s->grid, st));
-    CK(cudaEventRecord(s->ev0, st));
-    int ml = 0;
-    CK(viso_launch_match(s->match_jobs, 3 * F - 2, max_n, max_n, mp, s->grid, s->pairs, s->pending, st, &ml));
-    CK(cudaEventRecord(s->ev1, st));
-    CK(viso_launch_sort(s->sort_jobs, F, max_nL, pd, st));
-    ctx->launches += (max_n > 0 ? 2 : 0) + ml + 1;
-    if (F > 1) {
-        CK(viso_launch_circle(s->circ_jobs + 1, F - 1, st));
-        ctx->launches += 1;
-        int nl = 0;
-        CK(viso_launch_ransac(s->probs + 1, F - 1, param->ransac_iter, max_nL, pd, st, &nl));
-        ctx->launches += nl;
+    int nl = 0;
+    if (any_f32 && max_n > 0) { CK(viso_launch_pack(s->pack_jobs + 2 * t0, 2 * nf, max_n, s->dlen, s->err, st)); ++nl; }
+    if (any_img && max_n > 0) {
+        CK(viso_launch_extract(s->extract_jobs + 2 * t0, 2 * nf, max_n, s->img_w, s->img_h, s->img_w, 5, st));
+        ++nl;
     }
+    CK(viso_launch_grid(s->grid_jobs + 2 * t0, 2 * nf, s->grid, st));
+    ++nl;
+    /* match jobs: frame 0 has one (stereo), frame t >= 1 has three (stereo, temporal L, temporal R) */
+    const int mj0 = t0 == 0 ? 0 : 3 * t0 - 2, mj1 = 3 * t1 - 2;
+    CK(cudaEventRecord(s->ev0, st));
+    CK(viso_launch_match(s->match_jobs + mj0, mj1 - mj0, max_n, max_nt, mp, s->grid, s->pairs, s->pending, st, &nl));
+    CK(cudaEventRecord(s->ev1, st));
+    CK(viso_launch_sort(s->sort_jobs + t0, nf, max_nL, pd, st));
+    ++nl;
+    const int c0 = std::max(t0, 1);
+    if (t1 > c0) {
+        CK(viso_launch_circle(s->circ_jobs + c0, t1 - c0, st));
+        ++nl;
+        CK(viso_launch_ransac(s->probs + c0, t1 - c0, param->ransac_iter, max_nL, pd, st, &nl));
+    }
+    ctx->launches += nl;
+    CK(cudaEventRecord(s->ev_compute, st));
+    s->run_hi = std::max(s->run_hi, t1);
     s->have_ms = max_n > 0;
     s->ran = true;
     return VISO_OK;
+}
+
+int viso_seq_run_resident(viso_seq* s, const viso_param* param)
+{
+    if (!s) return VISO_ERR_ARG;
+    return viso_seq_run_range(s, param, 0, s->F);
 }
 
 int viso_seq_run(viso_seq* s, const viso_param* param, const uint32_t* seeds)
@@ -1199,6 +1353,7 @@ int viso_seq_download(viso_seq* s, viso_record* records)
     CK(cudaMemcpyAsync(records, s->rec, (size_t)s->F * sizeof(viso_record), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&flags, s->err, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    s->run_hi = 0;
     std::memset(&records[0], 0, sizeof(viso_record)); /* first frame: no pose (viso.cpp:1256-1260) */
     records[0].best_hyp = -1;
     return status_from_flags(ctx, flags);
@@ -1252,6 +1407,20 @@ int viso_seq_get_dense(viso_seq* s, int which, int t, int32_t* out4, int32_t* n)
     const int4* src = (which == 0 ? s->dense_lr : which == 1 ? s->dense_11 : s->dense_22) + (size_t)t * s->cap;
     *n = cnt;
     if (cnt > 0) CK(cudaMemcpyAsync(out4, src, (size_t)cnt * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VISO_OK;
+}
+
+int viso_seq_get_packed(viso_seq* s, int t, int side, uint16_t* rows, int32_t* n)
+{
+    if (!s) return VISO_ERR_ARG;
+    viso_ctx* ctx = s->ctx;
+    if (t < 0 || t >= s->F || side < 0 || side > 1 || !rows || !n) return ctx->fail(VISO_ERR_ARG, "seq_get_packed: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    const int cnt = side ? s->h_nR[t] : s->h_nL[t];
+    const uint16_t* src = (side ? s->dRu : s->dLu) + (size_t)t * s->cap * VISO_DESC_U16;
+    *n = cnt;
+    if (cnt > 0) CK(cudaMemcpyAsync(rows, src, (size_t)cnt * VISO_DESC_U16 * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return VISO_OK;
 }

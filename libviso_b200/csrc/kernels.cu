@@ -76,6 +76,7 @@ __device__ __forceinline__ int block_compact_slot(bool flag, int& base_io, int* 
 __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restrict__ jobs, int dlen, int* err)
 {
     const PackJob job = jobs[blockIdx.y];
+    if (job.from_image && *job.from_image) return;
     const int n = *job.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int row = blockIdx.x * 8 + warp; row < n; row += gridDim.x * 8) {
@@ -103,6 +104,60 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
         const unsigned tot = warp_sum_u(sum);
         if (lane == 0) job.rsum[row] = tot;
         if (bad) atomicOr(err, 1);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ extract */
+
+/*
+ * MyFeatureExtractor::computeImpl, viso.cpp:1004-1024, fused with the packing above: for keypoint k with
+ * p = Point2i(kp.pt) (cv::saturate_cast = round half to even, :1013), element (i, j), i, j in [-R, R] row-major, is
+ *     (p.y+i > 0 && p.y+i < rows && p.x+j > 0 && p.x+j < cols) ? sobel_x(p.y+i, p.x+j) : 0        (:1018)
+ * with sobel_x = cv::Sobel(image, CV_32F, 1, 0, 3, 1, 0, BORDER_REFLECT_101) (:1010), i.e. the integer
+ *     (I(y-1,x+1) + 2 I(y,x+1) + I(y+1,x+1)) - (I(y-1,x-1) + 2 I(y,x-1) + I(y+1,x-1)),  index -1 -> 1, n -> n-2.
+ * Values are integers in [-1020, 1020]; the row is written biased (+1024) in the u16 layout with its sum.
+ * One warp per keypoint, lane l owns elements 4l..4l+3; the image is read through L1/L2 (466 KB per image).
+ */
+__global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __restrict__ jobs, int width, int height,
+                                                           int pitch, int radius)
+{
+    const ExtractJob job = jobs[blockIdx.y];
+    if (!*job.from_image) return;
+    const int n = *job.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int side = 2 * radius + 1, dlen = side * side;
+    for (int row = blockIdx.x * 8 + warp; row < n; row += gridDim.x * 8) {
+        const float2 kp = job.kp[row];
+        const int px = __float2int_rn(kp.x), py = __float2int_rn(kp.y);
+        unsigned u[4];
+        unsigned sum = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = lane * 4 + e;
+            unsigned v = 0;
+            if (k < dlen) {
+                const int y = py + k / side - radius, x = px + k % side - radius;
+                int sob = 0;
+                if (y > 0 && y < height && x > 0 && x < width) {
+                    const int ym = y - 1, yp = (y + 1 < height) ? y + 1 : height - 2;
+                    const int xm = x - 1, xp = (x + 1 < width) ? x + 1 : width - 2;
+                    const unsigned char* r0 = job.img + (size_t)ym * pitch;
+                    const unsigned char* r1 = job.img + (size_t)y * pitch;
+                    const unsigned char* r2 = job.img + (size_t)yp * pitch;
+                    sob = ((int)__ldg(r0 + xp) + 2 * (int)__ldg(r1 + xp) + (int)__ldg(r2 + xp)) -
+                          ((int)__ldg(r0 + xm) + 2 * (int)__ldg(r1 + xm) + (int)__ldg(r2 + xm));
+                }
+                v = (unsigned)(sob + 1024);
+            }
+            u[e] = v;
+            sum += v;
+        }
+        uint2 w;
+        w.x = u[0] | (u[1] << 16);
+        w.y = u[2] | (u[3] << 16);
+        reinterpret_cast<uint2*>(job.out + (size_t)row * VISO_DESC_U16)[lane] = w;
+        const unsigned tot = warp_sum_u(sum);
+        if (lane == 0) job.rsum[row] = tot;
     }
 }
 
@@ -1642,6 +1697,15 @@ cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dle
     if (n_jobs <= 0 || max_n <= 0) return cudaSuccess;
     dim3 grid((max_n + 7) / 8, n_jobs);
     pack_desc_kernel<<<grid, 256, 0, s>>>(jobs, dlen, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_extract(const ExtractJob* jobs, int n_jobs, int max_n, int width, int height, int pitch, int radius,
+                                cudaStream_t s)
+{
+    if (n_jobs <= 0 || max_n <= 0) return cudaSuccess;
+    dim3 grid((max_n + 7) / 8, n_jobs);
+    extract_desc_kernel<<<grid, 256, 0, s>>>(jobs, width, height, pitch, radius);
     return cudaGetLastError();
 }
 

@@ -71,6 +71,17 @@ struct PackJob {
     const int* n;
     uint16_t* out;           /* n x 128 u16 */
     unsigned* rsum;          /* n row sums */
+    const int* from_image;   /* != 0: this set's descriptors come from extract_desc_kernel, skip */
+};
+
+/* MyFeatureExtractor::computeImpl on the device (viso.cpp:1004-1024): 8-bit image -> packed descriptor rows */
+struct ExtractJob {
+    const unsigned char* img; /* rows x pitch */
+    const float2* kp;
+    const int* n;
+    uint16_t* out;            /* n x 128 u16 */
+    unsigned* rsum;
+    const int* from_image;    /* == 0: skip (descriptors were uploaded as f32 rows) */
 };
 
 struct GridJob {
@@ -143,6 +154,8 @@ struct CircleJob {             /* per frame pair */
 
 /* launch wrappers (kernels.cu).  All enqueue on `s` and return cudaGetLastError(). */
 cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dlen, int* err_flag, cudaStream_t s);
+cudaError_t viso_launch_extract(const ExtractJob* jobs, int n_jobs, int max_n, int width, int height, int pitch, int radius,
+                                cudaStream_t s);
 cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStream_t s);
 cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
                               GridCfg g, unsigned long long* sad_pairs, int* n_pending, cudaStream_t s, int* launches);

@@ -169,7 +169,7 @@ def make_frame(pose, tex, n_features, noise_rng):
     imR = render(R, p + R @ np.array([BASE, 0.0, 0.0]), tex, noise_rng)
     kpL = detect_harris_binned(imL, n_features)
     kpR = detect_harris_binned(imR, n_features)
-    return dict(kpL=kpL, kpR=kpR, dL=extract_descriptors(imL, kpL), dR=extract_descriptors(imR, kpR))
+    return dict(kpL=kpL, kpR=kpR, dL=extract_descriptors(imL, kpL), dR=extract_descriptors(imR, kpR), imL=imL, imR=imR)
 
 
 def _seq_worker(args):

@@ -405,3 +405,72 @@ def test_sequence_pipeline(ctx, api, oracle, small_sequence):
     mb, pairs, evaluated = seq.stats()
     assert mb > 0 and 0 < evaluated <= pairs
     seq.close()
+
+
+# ------------------------------------------------------------------------------------------------ device front-end
+
+def test_device_extractor_matches_reference_descriptors(ctx, api, small_sequence):
+    """MyFeatureExtractor on the device (viso.cpp:1004-1024): packed rows == the cv::Sobel-based descriptors + 1024,
+    including keypoints on / outside the border and non-integral coordinates (Point2i rounding)"""
+    from libviso_b200 import synth
+    frames, _ = small_sequence
+    f = frames[2]
+    rng = np.random.default_rng(5)
+    H, W = f["imL"].shape
+    extra = np.array([[0, 0], [1, 1], [W - 1, H - 1], [W - 2, 3], [5, H - 1], [0.5, 1.5], [2.5, 3.5], [100.49, 50.51],
+                      [W + 3, 10], [-4, 7], [300, H + 2]], np.float32)
+    kpL = np.concatenate([f["kpL"], extra, (rng.random((40, 2)) * [W, H]).astype(np.float32)])
+    kpR = np.concatenate([f["kpR"], extra])
+    seq = ctx.sequence(2, len(kpL) + 8, 121, 8)
+    seq.set_image_size(W, H)
+    seq.upload_frame_images(0, f["imL"], f["imR"], kpL, kpR)
+    seq.upload_frame_images(1, f["imL"], f["imR"], kpL, kpR)
+    seq.set_calib(*synth.kitti_calib())
+    seq.run(api.param_default(ransac_iter=8), make_seeds(2, 8))
+    ctx.sync()
+    for side, (img, kp) in enumerate(((f["imL"], kpL), (f["imR"], kpR))):
+        want = synth.extract_descriptors(img, kp).astype(np.int32) + 1024
+        got = seq.get_packed(0, side).astype(np.int32)
+        assert got.shape == (len(kp), 128)
+        assert np.array_equal(got[:, :121], want)
+        assert (got[:, 121:] == 0).all()
+    seq.close()
+
+
+def test_sequence_from_images_and_chunked_ranges(ctx, api, oracle, small_sequence):
+    """images + keypoints in, chunked run_range() submissions: records identical to the one-shot f32-descriptor run
+    and to the oracle"""
+    from libviso_b200 import synth
+    frames, _ = small_sequence
+    P1, P2 = synth.kitti_calib()
+    H = 50
+    seeds = make_seeds(len(frames), H)
+    po = oracle.param_default(ransac_iter=H)
+    o = oracle.sequence(frames, P1, P2, po, seeds)
+    pg = api.param_default(ransac_iter=H)
+    cap = max(max(len(f["kpL"]), len(f["kpR"])) for f in frames)
+    seq = ctx.sequence(len(frames), cap, 121, H)
+    seq.set_calib(P1, P2)
+    seq.set_image_size(synth.W, synth.H)
+    seq.set_seeds(seeds, H)
+    # chunks of 2 frames; frames 2,3 arrive as f32 descriptors, the others as images
+    for t0 in range(0, len(frames), 2):
+        for t in range(t0, min(t0 + 2, len(frames))):
+            f = frames[t]
+            if t in (2, 3):
+                seq.upload_frame(t, f["kpL"], f["kpR"], f["dL"], f["dR"])
+            else:
+                seq.upload_frame_images(t, f["imL"], f["imR"], f["kpL"], f["kpR"])
+        seq.run_range(pg, t0, min(t0 + 2, len(frames)))
+    rec = seq.download()
+    for k in ("ok", "n_inliers", "n_circ", "best_hyp"):
+        assert np.array_equal(rec[k], o["records"][k]), k
+    assert_tr_close(rec["tr"], o["records"]["tr"])
+    # re-upload + re-run without an intervening host sync must wait for the kernels still reading the frames
+    for rep in range(2):
+        for t, f in enumerate(frames):
+            seq.upload_frame_images(t, f["imL"], f["imR"], f["kpL"], f["kpR"])
+        seq.run(pg)
+    rec2 = seq.download()
+    assert rec2.tobytes() == rec.tobytes()
+    seq.close()
