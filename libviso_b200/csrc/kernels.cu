@@ -23,6 +23,7 @@
 
 #include <math_constants.h>
 #include <stdlib.h>
+#include <algorithm>
 
 #define FULL 0xffffffffu
 
@@ -116,48 +117,91 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
  * with sobel_x = cv::Sobel(image, CV_32F, 1, 0, 3, 1, 0, BORDER_REFLECT_101) (:1010), i.e. the integer
  *     (I(y-1,x+1) + 2 I(y,x+1) + I(y+1,x+1)) - (I(y-1,x-1) + 2 I(y,x-1) + I(y+1,x-1)),  index -1 -> 1, n -> n-2.
  * Values are integers in [-1020, 1020]; the row is written biased (+1024) in the u16 layout with its sum.
- * One warp per keypoint, lane l owns elements 4l..4l+3; the image is read through L1/L2 (466 KB per image).
+ * One warp per keypoint.  The (2R+3)^2 source window is first staged in shared memory with the reflection already
+ * applied (6 byte loads per lane, ~3 image rows per load instruction instead of 11), then lane l computes elements
+ * 4l..4l+3 from the staged window.
  */
-__global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __restrict__ jobs, int width, int height,
-                                                           int pitch, int radius)
+#define VISO_EXTRACT_WIN 16 /* staged window pitch; supports radius <= 6 (2R+3 <= 15) */
+
+__device__ __forceinline__ int reflect101(int i, int n)
 {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return min(max(i, 0), n - 1); /* far outside: any in-range pixel, the sample is masked to 0 anyway */
+}
+
+#define VISO_EXTRACT_KPW 4 /* keypoints per warp iteration: their image loads are all in flight together */
+
+template <int radius>
+__global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __restrict__ jobs, int width, int height, int pitch)
+{
+    __shared__ unsigned char win_s[8][VISO_EXTRACT_KPW][VISO_EXTRACT_WIN * VISO_EXTRACT_WIN];
     const ExtractJob job = jobs[blockIdx.y];
     if (!*job.from_image) return;
     const int n = *job.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int side = 2 * radius + 1, dlen = side * side;
-    for (int row = blockIdx.x * 8 + warp; row < n; row += gridDim.x * 8) {
-        const float2 kp = job.kp[row];
-        const int px = __float2int_rn(kp.x), py = __float2int_rn(kp.y);
-        unsigned u[4];
-        unsigned sum = 0;
+    constexpr int side = 2 * radius + 1, dlen = side * side, wside = side + 2, wn = wside * wside;
+    constexpr int NL = (wn + 31) / 32;
+    for (int row0 = (blockIdx.x * 8 + warp) * VISO_EXTRACT_KPW; row0 < n; row0 += gridDim.x * 8 * VISO_EXTRACT_KPW) {
+        int px[VISO_EXTRACT_KPW], py[VISO_EXTRACT_KPW];
+        unsigned char pix[VISO_EXTRACT_KPW][NL];
+        /* the image is touched once per frame, so these loads mostly miss to DRAM: issue all of them first */
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k = lane * 4 + e;
-            unsigned v = 0;
-            if (k < dlen) {
-                const int y = py + k / side - radius, x = px + k % side - radius;
-                int sob = 0;
-                if (y > 0 && y < height && x > 0 && x < width) {
-                    const int ym = y - 1, yp = (y + 1 < height) ? y + 1 : height - 2;
-                    const int xm = x - 1, xp = (x + 1 < width) ? x + 1 : width - 2;
-                    const unsigned char* r0 = job.img + (size_t)ym * pitch;
-                    const unsigned char* r1 = job.img + (size_t)y * pitch;
-                    const unsigned char* r2 = job.img + (size_t)yp * pitch;
-                    sob = ((int)__ldg(r0 + xp) + 2 * (int)__ldg(r1 + xp) + (int)__ldg(r2 + xp)) -
-                          ((int)__ldg(r0 + xm) + 2 * (int)__ldg(r1 + xm) + (int)__ldg(r2 + xm));
-                }
-                v = (unsigned)(sob + 1024);
+        for (int q = 0; q < VISO_EXTRACT_KPW; ++q) {
+            const float2 kp = job.kp[min(row0 + q, n - 1)];
+            px[q] = __float2int_rn(kp.x); py[q] = __float2int_rn(kp.y);
+#pragma unroll
+            for (int j = 0; j < NL; ++j) {
+                const int idx = min(lane + 32 * j, wn - 1);
+                const int wy = idx / wside, wx = idx - wy * wside;
+                const int iy = reflect101(py[q] - radius - 1 + wy, height), ix = reflect101(px[q] - radius - 1 + wx, width);
+                pix[q][j] = __ldg(job.img + (size_t)iy * pitch + ix);
             }
-            u[e] = v;
-            sum += v;
         }
-        uint2 w;
-        w.x = u[0] | (u[1] << 16);
-        w.y = u[2] | (u[3] << 16);
-        reinterpret_cast<uint2*>(job.out + (size_t)row * VISO_DESC_U16)[lane] = w;
-        const unsigned tot = warp_sum_u(sum);
-        if (lane == 0) job.rsum[row] = tot;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < VISO_EXTRACT_KPW; ++q)
+#pragma unroll
+            for (int j = 0; j < NL; ++j) {
+                const int idx = lane + 32 * j;
+                if (idx < wn) {
+                    const int wy = idx / wside, wx = idx - wy * wside;
+                    win_s[warp][q][wy * VISO_EXTRACT_WIN + wx] = pix[q][j];
+                }
+            }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < VISO_EXTRACT_KPW; ++q) {
+            const int row = row0 + q;
+            if (row >= n) break; /* warp uniform */
+            const unsigned char* win = win_s[warp][q];
+            unsigned u[4];
+            unsigned sum = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = lane * 4 + e;
+                unsigned v = 0;
+                if (k < dlen) {
+                    const int r = k / side, c = k - r * side;
+                    const int y = py[q] + r - radius, x = px[q] + c - radius;
+                    int sob = 0;
+                    if (y > 0 && y < height && x > 0 && x < width) {
+                        const unsigned char* w0 = win + r * VISO_EXTRACT_WIN + c; /* window row r = image row y-1 */
+                        sob = ((int)w0[2] + 2 * (int)w0[VISO_EXTRACT_WIN + 2] + (int)w0[2 * VISO_EXTRACT_WIN + 2]) -
+                              ((int)w0[0] + 2 * (int)w0[VISO_EXTRACT_WIN] + (int)w0[2 * VISO_EXTRACT_WIN]);
+                    }
+                    v = (unsigned)(sob + 1024);
+                }
+                u[e] = v;
+                sum += v;
+            }
+            uint2 w;
+            w.x = u[0] | (u[1] << 16);
+            w.y = u[2] | (u[3] << 16);
+            reinterpret_cast<uint2*>(job.out + (size_t)row * VISO_DESC_U16)[lane] = w;
+            const unsigned tot = warp_sum_u(sum);
+            if (lane == 0) job.rsum[row] = tot;
+        }
     }
 }
 
@@ -877,8 +921,8 @@ sad_match_generic_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch& ws = wscr[warp];
     unsigned pairs = 0;
-    const int q_end = min(nq, (int)(blockIdx.x + 1) * VISO_STRIP_QPC);
-    for (int qi = blockIdx.x * VISO_STRIP_QPC + warp; qi < q_end; qi += VISO_MATCH_WARPS) {
+    for (int chunk = blockIdx.x; chunk * VISO_STRIP_QPC < nq; chunk += gridDim.x)
+    for (int qi = chunk * VISO_STRIP_QPC + warp; qi < min(nq, (chunk + 1) * VISO_STRIP_QPC); qi += VISO_MATCH_WARPS) {
         const uint4 qrec = __ldg(job.q.srec + qi);
         if (only_pending && job.out[qrec.z].w != VISO_PENDING) continue;
         if (nt <= 0) {
@@ -1349,11 +1393,74 @@ __device__ __forceinline__ void sample_from_seeds(const uint32_t* seeds, int N, 
     s[0] = s0; s[1] = s1; s[2] = s2;
 }
 
+__constant__ int c_pair_a[27] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 0, 1, 2, 3, 4, 5};
+__constant__ int c_pair_b[27] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 6, 6, 6, 6, 6, 6};
+
+/* One Jacobian row + weighted residual of one point: row r of point_rows() with exactly the same expressions
+ * (viso.cpp:1441-1495).  out: 6 Jacobian columns + residual. */
+__device__ __forceinline__ void point_row(const Rot& R, const ParamDev& P, double X1p, double Y1p, double Z1p,
+                                          double weight, double ob_r, int r, double out[7])
+{
+    const double X1c = R.r00 * X1p + R.r01 * Y1p + R.r02 * Z1p + R.tx;
+    const double Y1c = R.r10 * X1p + R.r11 * Y1p + R.r12 * Z1p + R.ty;
+    const double Z1c = R.r20 * X1p + R.r21 * Y1p + R.r22 * Z1p + R.tz;
+    const double X2c = X1c - P.base;
+    const bool xrow = (r == 0 || r == 2);
+    const double num_c = (r == 2) ? X2c : (xrow ? X1c : Y1c); /* the camera coordinate the row differentiates */
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double X1cd, Y1cd, Z1cd;
+        switch (j) {
+        case 0: X1cd = 0;
+            Y1cd = R.rdrx10 * X1p + R.rdrx11 * Y1p + R.rdrx12 * Z1p;
+            Z1cd = R.rdrx20 * X1p + R.rdrx21 * Y1p + R.rdrx22 * Z1p;
+            break;
+        case 1: X1cd = R.rdry00 * X1p + R.rdry01 * Y1p + R.rdry02 * Z1p;
+            Y1cd = R.rdry10 * X1p + R.rdry11 * Y1p + R.rdry12 * Z1p;
+            Z1cd = R.rdry20 * X1p + R.rdry21 * Y1p + R.rdry22 * Z1p;
+            break;
+        case 2: X1cd = R.rdrz00 * X1p + R.rdrz01 * Y1p;
+            Y1cd = R.rdrz10 * X1p + R.rdrz11 * Y1p;
+            Z1cd = R.rdrz20 * X1p + R.rdrz21 * Y1p;
+            break;
+        case 3: X1cd = 1; Y1cd = 0; Z1cd = 0; break;
+        case 4: X1cd = 0; Y1cd = 1; Z1cd = 0; break;
+        default: X1cd = 0; Y1cd = 0; Z1cd = 1; break;
+        }
+        const double dnum = xrow ? X1cd : Y1cd;
+        out[j] = weight * P.f * (dnum * Z1c - num_c * Z1cd) / (Z1c * Z1c);
+    }
+    const double pred = (r == 2) ? P.f * X2c / Z1c + P.cu : (xrow ? P.f * X1c / Z1c + P.cu : P.f * Y1c / Z1c + P.cv);
+    out[6] = weight * (ob_r - pred);
+}
+
+/* viso.cpp:1406-1424 with the six sin / cos evaluated by six lanes of the warp and broadcast (same values as
+ * make_rot: each is one call of the same function on the same argument) */
+__device__ __forceinline__ void make_rot_warp(const double* tr, Rot& R, int lane)
+{
+    double v = 0;
+    if (lane < 6) v = (lane & 1) ? cos(tr[lane >> 1]) : sin(tr[lane >> 1]);
+    const double sx = __shfl_sync(FULL, v, 0), cx = __shfl_sync(FULL, v, 1), sy = __shfl_sync(FULL, v, 2);
+    const double cy = __shfl_sync(FULL, v, 3), sz = __shfl_sync(FULL, v, 4), cz = __shfl_sync(FULL, v, 5);
+    R.tx = tr[3]; R.ty = tr[4]; R.tz = tr[5];
+    R.r00 = +cy * cz;                R.r01 = -cy * sz;                R.r02 = +sy;
+    R.r10 = +sx * sy * cz + cx * sz; R.r11 = -sx * sy * sz + cx * cz; R.r12 = -sx * cy;
+    R.r20 = -cx * sy * cz + sx * sz; R.r21 = +cx * sy * sz + sx * cz; R.r22 = +cx * cy;
+    R.rdrx10 = +cx * sy * cz - sx * sz; R.rdrx11 = -cx * sy * sz - sx * cz; R.rdrx12 = -cx * cy;
+    R.rdrx20 = +sx * sy * cz + cx * sz; R.rdrx21 = -sx * sy * sz + cx * cz; R.rdrx22 = -sx * cy;
+    R.rdry00 = -sy * cz;      R.rdry01 = +sy * sz;      R.rdry02 = +cy;
+    R.rdry10 = +sx * cy * cz; R.rdry11 = -sx * cy * sz; R.rdry12 = +sx * sy;
+    R.rdry20 = -cx * cy * cz; R.rdry21 = +cx * cy * sz; R.rdry22 = -cx * sy;
+    R.rdrz00 = -cy * sz;                R.rdrz01 = -cy * cz;
+    R.rdrz10 = -sx * sy * sz + cx * cz; R.rdrz11 = -sx * sy * cz - cx * sz;
+    R.rdrz20 = +cx * sy * sz + sx * cz; R.rdrz21 = +cx * sy * cz - sx * sz;
+}
+
 /*
  * One thread per hypothesis: tr = 0, 3-point sample, Gauss-Newton (minimize_reproj with 3 active points),
  * viso.cpp:1555-1562 + 1583-1623.  Sums run in the reference's row order 0..11.
  */
-__global__ void __launch_bounds__(64) ransac_hyp_kernel(const RansacProb* __restrict__ probs, ParamDev P)
+__global__ void __launch_bounds__(32) ransac_hyp_kernel(const RansacProb* __restrict__ probs, ParamDev P)
 {
     const RansacProb& pb = probs[blockIdx.y];
     const int hId = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1388,7 +1495,7 @@ __global__ void __launch_bounds__(64) ransac_hyp_kernel(const RansacProb* __rest
 #pragma unroll
                 for (int j = 0; j < 6; ++j) A[i][j] = 0;
             }
-#pragma unroll 1
+#pragma unroll
             for (int i = 0; i < 3; ++i) {
                 double rows[4][7];
                 point_rows(R, P, Xs[i][0], Xs[i][1], Xs[i][2], w[i], Os[i], rows);
@@ -1442,9 +1549,6 @@ __global__ void __launch_bounds__(256) ransac_score_kernel(const RansacProb* __r
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
     if (lane == 0) pb.hyp_count[hId] = cnt;
 }
-
-__constant__ int c_pair_a[27] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 0, 1, 2, 3, 4, 5};
-__constant__ int c_pair_b[27] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 6, 6, 6, 6, 6, 6};
 
 /*
  * Block-cooperative minimize_reproj (viso.cpp:1583-1623) over an arbitrary active set.  Per iteration:
@@ -1704,8 +1808,9 @@ cudaError_t viso_launch_extract(const ExtractJob* jobs, int n_jobs, int max_n, i
                                 cudaStream_t s)
 {
     if (n_jobs <= 0 || max_n <= 0) return cudaSuccess;
-    dim3 grid((max_n + 7) / 8, n_jobs);
-    extract_desc_kernel<<<grid, 256, 0, s>>>(jobs, width, height, pitch, radius);
+    dim3 grid((max_n + 8 * VISO_EXTRACT_KPW - 1) / (8 * VISO_EXTRACT_KPW), n_jobs);
+    if (radius != 5) return cudaErrorInvalidValue; /* the pipeline's descriptor radius (viso.cpp:1174) */
+    extract_desc_kernel<5><<<grid, 256, 0, s>>>(jobs, width, height, pitch);
     return cudaGetLastError();
 }
 
@@ -1730,7 +1835,9 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
         const char* m = getenv("VISO_MATCH_MODE");
         mode = (m && m[0] == 'g') ? 1 : 0;
     }
-    const dim3 ggrid((max_nq + VISO_STRIP_QPC - 1) / VISO_STRIP_QPC, n_jobs);
+    /* the generic kernel loops over query chunks: about 16 CTAs per SM in total, never more than one per chunk */
+    const int gchunks = (max_nq + VISO_STRIP_QPC - 1) / VISO_STRIP_QPC;
+    const dim3 ggrid(std::min(gchunks, std::max(1, (148 * 16 + n_jobs - 1) / n_jobs)), n_jobs);
     if (mode == 1) {
         sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, n_pending, 0);
         if (launches) *launches += 1;
@@ -1791,7 +1898,7 @@ cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, 
                                int* launches)
 {
     if (n_probs <= 0 || max_H <= 0) return cudaSuccess;
-    ransac_hyp_kernel<<<dim3((max_H + 63) / 64, n_probs), 64, 0, s>>>(probs, p);
+    ransac_hyp_kernel<<<dim3((max_H + 31) / 32, n_probs), 32, 0, s>>>(probs, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ransac_score_kernel<<<dim3((max_H + 7) / 8, n_probs), 256, 0, s>>>(probs, p);
