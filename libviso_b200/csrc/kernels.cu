@@ -428,8 +428,26 @@ struct BestState {
 /* one batch of NS*4 candidates starting at list entry `base` (NS = 8: up to 32, NS = 4: up to 16).  Branch free:
  * entries past the end of the list are clamped to the last one (a repeated L1-hit load) and masked afterwards, so
  * that all 2*NS row loads of the batch can be in flight together. */
-template <int NS>
-__device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, const WarpScratch& ws, int base, int n, int lane,
+/* where the candidates of a query come from: target index of entry e, and (index, L1 distance bits, row sum) */
+struct ListAcc { /* the warp's uint4 list (generic kernel) */
+    const WarpScratch& ws;
+    __device__ __forceinline__ unsigned index(int e) const { return ws.list[e].x; }
+    __device__ __forceinline__ uint4 entry(int e) const { return ws.list[e]; }
+};
+struct TileAcc { /* region indices into the staged neighbourhood (tile kernel): the distance is recomputed */
+    const unsigned short* ql;
+    const uint4* reg;
+    float qx, qy;
+    __device__ __forceinline__ unsigned index(int e) const { return reg[ql[e]].z; }
+    __device__ __forceinline__ uint4 entry(int e) const
+    {
+        const uint4 r = reg[ql[e]];
+        return make_uint4(r.z, __float_as_uint(l1_dist(qx, qy, __uint_as_float(r.x), __uint_as_float(r.y))), r.w, 0u);
+    }
+};
+
+template <int NS, class Acc>
+__device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, const Acc& acc_, int base, int n, int lane,
                                            const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
 {
     const int sub = lane & 7, g = lane >> 3;
@@ -441,7 +459,7 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
 #pragma unroll
         for (int s = 0; s < VISO_EVAL_DEPTH; ++s) {
             const int e = min(base + 4 * (h + s) + g, n - 1);
-            const unsigned idx = ws.list[e].x;
+            const unsigned idx = acc_.index(e);
             const uint4* rp = tbase + (size_t)idx * (VISO_DESC_U16 / 8);
             ra[s] = __ldg(rp);
             rb[s] = __ldg(rp + 8);
@@ -488,7 +506,7 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
     unsigned sad = 0xffffffffu, dbits = 0;
     int idx = -1;
     if (e < n) {
-        const uint4 le = ws.list[e];
+        const uint4 le = acc_.entry(e);
         sad = qsum + le.z - 2u * tot;
         dbits = le.y;
         idx = (int)le.x;
@@ -509,13 +527,14 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
     }
 }
 
-__device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, const WarpScratch& ws, int n, int lane,
+template <class Acc>
+__device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, const Acc& acc, int n, int lane,
                                           const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
 {
     const uint4* tbase = reinterpret_cast<const uint4*>(tdesc) + (lane & 7);
     int base = 0;
-    for (; n - base > 16; base += 32) eval_batch<8>(tbase, ws, base, n, lane, qa, qb, qsum, st);
-    if (base < n) eval_batch<4>(tbase, ws, base, n, lane, qa, qb, qsum, st);
+    for (; n - base > 16; base += 32) eval_batch<8>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+    if (base < n) eval_batch<4>(tbase, acc, base, n, lane, qa, qb, qsum, st);
 }
 
 /* viso.cpp:711-722: the ratio test and the dense output record (best_idx, best_d1, best_d2, valid) */
@@ -683,7 +702,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
         nlist += __popc(tm);
         if (nlist > VISO_LIST_CAP - 32) {
             __syncwarp();
-            eval_list(job.t.desc, ws, nlist, lane, qa, qb, qsum, st);
+            eval_list(job.t.desc, ListAcc{ws}, nlist, lane, qa, qb, qsum, st);
             pairs += nlist;
             nlist = 0;
             __syncwarp();
@@ -691,7 +710,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
     });
     if (nlist > 0) {
         __syncwarp();
-        eval_list(job.t.desc, ws, nlist, lane, qa, qb, qsum, st);
+        eval_list(job.t.desc, ListAcc{ws}, nlist, lane, qa, qb, qsum, st);
         pairs += nlist;
         __syncwarp();
     }
@@ -722,7 +741,6 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                  int* n_pending)
 {
     extern __shared__ uint4 reg[];                                /* staged neighbourhood, reg_cap records */
-    __shared__ WarpScratch wscr[VISO_MATCH_WARPS];
     __shared__ unsigned short qlist[32][VISO_QLIST_CAP + 2];      /* +2: odd word stride, lanes = queries write */
     __shared__ int qcnt[32];
     __shared__ int row_off[VISO_MAX_REG_ROWS + 1];
@@ -733,7 +751,6 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     const MatchParamsDev& P = mp.p[job.mode];
     const int nq = *job.q.n, nt = *job.t.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpScratch& ws = wscr[warp];
     const int tiles_x = (g.gx + VISO_TILE_W - 1) / VISO_TILE_W;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     if (ty * VISO_TILE_H >= g.gy || nq <= 0) return;
@@ -870,29 +887,28 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 const uint4 qa = __ldg(qp), qb = __ldg(qp + 8);
                 BestState st;
                 st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
-                int nlist = 0;
-                for (int base = 0; base < n; base += 32) {
-                    const int e = base + lane;
-                    bool take = e < n;
-                    const uint4 rec = reg[qlist[kk][take ? e : 0]];
-                    const float dist = l1_dist(qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
-                    if (P.epipolar) {
+                unsigned short* ql = qlist[kk];
+                int nlist = n;
+                if (P.epipolar) { /* Sampson gate (viso.cpp:695-701), lanes = candidates, compacting the list in place */
+                    nlist = 0;
+                    for (int base = 0; base < n; base += 32) {
+                        const int e = base + lane;
+                        bool take = e < n;
+                        const unsigned short ri = ql[take ? e : 0];
                         if (take) {
+                            const uint4 rec = reg[ri];
                             const double sd = sampson_dev(P.F, qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
                             if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
                         }
                         const unsigned tm = __ballot_sync(FULL, take);
-                        if (take) ws.list[nlist + __popc(tm & ((1u << lane) - 1))] = make_uint4(rec.z, __float_as_uint(dist), rec.w, 0u);
+                        __syncwarp(); /* every lane has read its entry before the slots are reused */
+                        if (take) ql[nlist + __popc(tm & ((1u << lane) - 1))] = ri;
                         nlist += __popc(tm);
-                    } else {
-                        if (take) ws.list[e] = make_uint4(rec.z, __float_as_uint(dist), rec.w, 0u);
-                        nlist = n;
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (nlist > 0) eval_list(job.t.desc, ws, nlist, lane, qa, qb, qrec.w, st);
+                if (nlist > 0) eval_list(job.t.desc, TileAcc{ql, reg, qx, qy}, nlist, lane, qa, qb, qrec.w, st);
                 pairs += nlist;
-                __syncwarp();
                 if (lane == 0) write_result(job, P, q, st);
             }
         }

@@ -28,7 +28,7 @@
 #define VISO_EVAL_DEPTH 4          /* SAD steps whose row loads are issued together (4 rows each) */
 #endif
 #ifndef VISO_MATCH_MINB
-#define VISO_MATCH_MINB 6          /* resident CTAs per SM the match kernels are compiled for */
+#define VISO_MATCH_MINB 8          /* resident CTAs per SM the match kernels are compiled for */
 #endif
 #define VISO_TILE_W 6            /* query tile of sad_match: 6 x 4 cells = 96 x 64 px */
 #define VISO_TILE_H 4
