@@ -446,35 +446,44 @@ struct TileAcc { /* region indices into the staged neighbourhood (tile kernel): 
     }
 };
 
-template <int NS, class Acc>
+/* NB = butterfly width in steps (8: up to 32 candidates, 4: up to 16), NL <= NB = steps whose rows are actually
+ * loaded and evaluated (the rest contribute 0 and are masked) */
+template <int NB, int NL, class Acc>
 __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, const Acc& acc_, int base, int n, int lane,
                                            const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
 {
     const int sub = lane & 7, g = lane >> 3;
     const bool b0 = sub & 1, b1 = sub & 2, b2 = sub & 4;
-    unsigned part[NS];
+    /* lane L fetches the record of candidate base + L once; the steps and the final fold get it by shuffle */
+    const uint4 ent = acc_.entry(min(base + lane, n - 1));
+    unsigned part[NB];
 #pragma unroll
-    for (int h = 0; h < NS; h += VISO_EVAL_DEPTH) { /* VISO_EVAL_DEPTH steps = 2*VISO_EVAL_DEPTH row loads in flight */
+    for (int s = 0; s < NB; ++s) part[s] = 0;
+#pragma unroll
+    for (int h = 0; h < NL; h += VISO_EVAL_DEPTH) { /* VISO_EVAL_DEPTH steps = 2*VISO_EVAL_DEPTH row loads in flight */
         uint4 ra[VISO_EVAL_DEPTH], rb[VISO_EVAL_DEPTH];
 #pragma unroll
         for (int s = 0; s < VISO_EVAL_DEPTH; ++s) {
-            const int e = min(base + 4 * (h + s) + g, n - 1);
-            const unsigned idx = acc_.index(e);
-            const uint4* rp = tbase + (size_t)idx * (VISO_DESC_U16 / 8);
-            ra[s] = __ldg(rp);
-            rb[s] = __ldg(rp + 8);
+            if (h + s < NL) {
+                const unsigned idx = __shfl_sync(FULL, ent.x, 4 * (h + s) + g);
+                const uint4* rp = tbase + (size_t)idx * (VISO_DESC_U16 / 8);
+                ra[s] = __ldg(rp);
+                rb[s] = __ldg(rp + 8);
+            }
         }
 #pragma unroll
         for (int s = 0; s < VISO_EVAL_DEPTH; ++s) {
-            const unsigned acc = __vminu2(qa.x, ra[s].x) + __vminu2(qa.y, ra[s].y) + __vminu2(qa.z, ra[s].z) + __vminu2(qa.w, ra[s].w) +
-                                 __vminu2(qb.x, rb[s].x) + __vminu2(qb.y, rb[s].y) + __vminu2(qb.z, rb[s].z) + __vminu2(qb.w, rb[s].w);
-            part[h + s] = (acc & 0xffffu) + (acc >> 16); /* 16 elements x 2047 < 65536: no carry between halves */
+            if (h + s < NL) {
+                const unsigned acc = __vminu2(qa.x, ra[s].x) + __vminu2(qa.y, ra[s].y) + __vminu2(qa.z, ra[s].z) + __vminu2(qa.w, ra[s].w) +
+                                     __vminu2(qb.x, rb[s].x) + __vminu2(qb.y, rb[s].y) + __vminu2(qb.z, rb[s].z) + __vminu2(qb.w, rb[s].w);
+                part[h + s] = (acc & 0xffffu) + (acc >> 16); /* 16 elements x 2047 < 65536: no carry between halves */
+            }
         }
     }
     /* transposed reduction over the 8 lanes of a row group: lane (g, sub) ends with candidate 4*step + g where
-     * step = sub (NS = 8) or sub & 3 (NS = 4; lanes sub and sub^4 then hold the same candidate) */
+     * step = sub (NB = 8) or sub & 3 (NB = 4; lanes sub and sub^4 then hold the same candidate) */
     unsigned r2[2];
-    if (NS == 8) {
+    if (NB == 8) {
         unsigned r4[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -494,22 +503,25 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
         }
     }
     unsigned tot;
-    int e;
-    if (NS == 8) {
+    int slot; /* position of this lane's candidate inside the batch */
+    bool mine = true;
+    if (NB == 8) {
         tot = (b2 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b2 ? r2[0] : r2[1], 4);
-        e = base + 4 * sub + g;
+        slot = 4 * sub + g;
     } else {
         const unsigned t2 = (b1 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b1 ? r2[0] : r2[1], 2);
         tot = t2 + __shfl_xor_sync(FULL, t2, 4);
-        e = b2 ? n : base + 4 * (sub & 3) + g; /* the duplicate lanes sit out */
+        slot = 4 * (sub & 3) + g;
+        mine = !b2; /* the duplicate lanes sit out */
     }
+    const unsigned cidx = __shfl_sync(FULL, ent.x, slot), cdist = __shfl_sync(FULL, ent.y, slot);
+    const unsigned csum = __shfl_sync(FULL, ent.z, slot);
     unsigned sad = 0xffffffffu, dbits = 0;
     int idx = -1;
-    if (e < n) {
-        const uint4 le = acc_.entry(e);
-        sad = qsum + le.z - 2u * tot;
-        dbits = le.y;
-        idx = (int)le.x;
+    if (mine && base + slot < n) {
+        sad = qsum + csum - 2u * tot;
+        dbits = cdist;
+        idx = (int)cidx;
     }
     const unsigned m1 = __reduce_min_sync(FULL, sad);
     const unsigned ties = __ballot_sync(FULL, sad == m1);
@@ -533,8 +545,11 @@ __device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, co
 {
     const uint4* tbase = reinterpret_cast<const uint4*>(tdesc) + (lane & 7);
     int base = 0;
-    for (; n - base > 16; base += 32) eval_batch<8>(tbase, acc, base, n, lane, qa, qb, qsum, st);
-    if (base < n) eval_batch<4>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+    for (; n - base > 24; base += 32) eval_batch<8, 8>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+    const int rest = n - base; /* 0..24: rows are loaded in units of 8 candidates */
+    if (rest > 16) eval_batch<8, 6>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+    else if (rest > 8) eval_batch<4, 4>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+    else if (rest > 0) eval_batch<4, 2>(tbase, acc, base, n, lane, qa, qb, qsum, st);
 }
 
 /* viso.cpp:711-722: the ratio test and the dense output record (best_idx, best_d1, best_d2, valid) */

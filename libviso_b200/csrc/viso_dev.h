@@ -25,7 +25,7 @@
 #define VISO_MATCH_WARPS 4
 #endif
 #ifndef VISO_EVAL_DEPTH
-#define VISO_EVAL_DEPTH 4          /* SAD steps whose row loads are issued together (4 rows each) */
+#define VISO_EVAL_DEPTH 2          /* SAD steps whose row loads are issued together (4 rows each) */
 #endif
 #ifndef VISO_MATCH_MINB
 #define VISO_MATCH_MINB 8          /* resident CTAs per SM the match kernels are compiled for */
