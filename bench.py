@@ -124,6 +124,17 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(args):
+    """DRAM bytes of one sad_match launch from the committed ncu capture of this exact config (else None)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["sad_match_kernel"]
+        if t["frames"] == args.frames and t["features"] == args.features:
+            return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def cpu_oracle_pairs(frames, order, t0, n_pairs, H, seeds):
     """run the CPU oracle over frames [t0, t0+n_pairs] of the long sequence; returns (seconds, records)"""
     from oracle import oracle
@@ -369,7 +380,9 @@ def main():
             "data": "synthetic", "config": workload_config(args),
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "sad_match_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(args), "peak_source": peak_src,
+                         "note": "HBM fraction as the contract defines it; the kernel is bound by the L1 data pipe (71% of peak "
+                                 "wavefronts) and the ALU pipe (53%), not by HBM: see DESIGN.md section 4",
                          "algorithmic_bytes_per_launch": int(match_bytes), "kernel_ms": mm,
                          "sad_pairs_per_launch": int(sad_pairs), "sad_evaluated_per_launch": int(sad_eval),
                          "kernel_share_of_step": mm / (dev_ms / args.steps)},
