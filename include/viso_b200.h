@@ -130,6 +130,12 @@ int viso_triangulate_rectified_f64(viso_ctx* ctx, const double* x, int m, double
 /* triangulate_rectified (float), reference src/mvg.cpp:172-192; x1,x2: 2 x m, X: 3 x m */
 int viso_triangulate_rectified_f32(viso_ctx* ctx, const float* x1, const float* x2, int m, double f, double base,
                                    double c1u, double c1v, float* X);
+/* triangulate_dlt, reference src/mvg.cpp:124-169; x1, x2: 2 x m float, P1, P2: 3 x 4 double, X: 3 x m float.  The
+ * null vector of a 4 x 4 SVD is unique only up to rounding: agreement with cv::SVD is ~1e-6 relative, not bitwise. */
+int viso_triangulate_dlt(viso_ctx* ctx, const float* x1, const float* x2, int m, const double P1[12], const double P2[12],
+                         float* X);
+/* solveRigidMotion, reference src/estimation.cpp:29-51 (Kabsch); A, B: 3 x n float; T: 4 x 4 float, T * B ~ A */
+int viso_solve_rigid_motion(viso_ctx* ctx, const float* A, const float* B, int n, float T[16]);
 /* projectPoints(X,P), reference src/viso.cpp:326-333 (e2h/h2e misc.h:90-124); X 3 x n, P 3x4, x 2 x n */
 int viso_project_points(viso_ctx* ctx, const double* X, int n, const double P[12], double* x);
 

@@ -221,6 +221,18 @@ class Context:
         self._ck(lib().viso_sort_matches(self.h, _p(m), len(m)))
         return m
 
+    # ---- triangulate_dlt (mvg.cpp:124-169), solveRigidMotion (estimation.cpp:29-51) ----
+    def triangulate_dlt(self, x1, x2, P1, P2):
+        x1, x2, P1, P2 = _f32(x1), _f32(x2), _f64(P1).reshape(12), _f64(P2).reshape(12)
+        m = x1.shape[1]; X = np.zeros((3, m), np.float32)
+        self._ck(lib().viso_triangulate_dlt(self.h, _p(x1), _p(x2), m, _p(P1), _p(P2), _p(X)))
+        return X
+
+    def solve_rigid_motion(self, A, B):
+        A, B = _f32(A), _f32(B); T = np.zeros((4, 4), np.float32)
+        self._ck(lib().viso_solve_rigid_motion(self.h, _p(A), _p(B), A.shape[1], _p(T)))
+        return T
+
     # ---- match_circle, viso.cpp:206-243 ----
     def match_circle(self, mlr, mlrp, m11, m22):
         mlr, mlrp, m11, m22 = (_i32(a).reshape(-1, 3) for a in (mlr, mlrp, m11, m22))

@@ -644,6 +644,60 @@ int viso_project_points(viso_ctx* ctx, const double* X, int n, const double P[12
     return status_from_flags(ctx, flags);
 }
 
+int viso_triangulate_dlt(viso_ctx* ctx, const float* x1, const float* x2, int m, const double P1[12], const double P2[12],
+                         float* X)
+{
+    if (!ctx) return VISO_ERR_ARG;
+    if (m < 0) return ctx->fail(VISO_ERR_ARG, "triangulate_dlt: bad argument");
+    if (m == 0) return VISO_OK;
+    if (!x1 || !x2 || !P1 || !P2 || !X) return ctx->fail(VISO_ERR_ARG, "triangulate_dlt: null input");
+    CK(cudaSetDevice(ctx->device));
+    struct Bufs { float *x1, *x2, *X; double *P1, *P2; } b;
+    auto carve = [&](Carver& c) {
+        b.x1 = c.take<float>((size_t)m * 2); b.x2 = c.take<float>((size_t)m * 2); b.X = c.take<float>((size_t)m * 3);
+        b.P1 = c.take<double>(12); b.P2 = c.take<double>(12);
+    };
+    Carver measure(nullptr);
+    carve(measure);
+    int rc = ensure_scratch(ctx, measure.off);
+    if (rc) return rc;
+    Carver real(ctx->d_scr);
+    carve(real);
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(b.x1, x1, (size_t)m * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.x2, x2, (size_t)m * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.P1, P1, 96, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.P2, P2, 96, cudaMemcpyHostToDevice, s));
+    CK(viso_launch_triangulate_dlt(b.x1, b.x2, m, b.P1, b.P2, b.X, s));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(X, b.X, (size_t)m * 12, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return VISO_OK;
+}
+
+int viso_solve_rigid_motion(viso_ctx* ctx, const float* A, const float* B, int n, float T[16])
+{
+    if (!ctx) return VISO_ERR_ARG;
+    if (n < 2 || !A || !B || !T) return ctx->fail(VISO_ERR_ARG, "solve_rigid_motion: needs at least 2 points (estimation.cpp:32)");
+    CK(cudaSetDevice(ctx->device));
+    struct Bufs { float *A, *B, *T; } b;
+    auto carve = [&](Carver& c) { b.A = c.take<float>((size_t)n * 3); b.B = c.take<float>((size_t)n * 3); b.T = c.take<float>(16); };
+    Carver measure(nullptr);
+    carve(measure);
+    int rc = ensure_scratch(ctx, measure.off);
+    if (rc) return rc;
+    Carver real(ctx->d_scr);
+    carve(real);
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(b.A, A, (size_t)n * 12, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.B, B, (size_t)n * 12, cudaMemcpyHostToDevice, s));
+    CK(viso_launch_rigid_motion(b.A, b.B, n, b.T, s));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(T, b.T, 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return VISO_OK;
+}
+
 /* ------------------------------------------------------------------------------------------------ estimation */
 
 int viso_get_inliers(viso_ctx* ctx, const double* X, const double* observe, int n, const double tr[6],

@@ -5,6 +5,8 @@
  * viso.cpp:87-107) that fills the RANSAC sample table.
  */
 #include "viso.h"
+#include "mvg.h"
+#include "estimation.h"
 
 #include "../../include/viso_b200.h"
 
@@ -255,6 +257,41 @@ Mat F_from_P(const Mat& P1, const Mat& P2)
     Mat F(3, 3, cv::DataType<double>::type);
     viso_F_from_P(P1.ptr<double>(0), P2.ptr<double>(0), 0, F.ptr<double>(0));
     return F;
+}
+
+/* reference src/mvg.cpp:124-169 */
+Mat triangulate_dlt(const Mat& x1, const Mat& x2, const Mat& P1, const Mat& P2)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    assert(x1.cols == x2.cols && x1.rows == 2 && x2.rows == 2);                                   /* mvg.cpp:127-129 */
+    assert(x1.type() == cv::DataType<float>::type && x2.type() == cv::DataType<float>::type);     /* :130-131 */
+    assert(P1.type() == cv::DataType<double>::type && P2.type() == cv::DataType<double>::type);   /* :132-133 */
+    Mat X(3, x1.cols, cv::DataType<float>::type);
+    if (x1.cols > 0)
+        ck(viso_triangulate_dlt(ctx(), x1.ptr<float>(0), x2.ptr<float>(0), x1.cols, P1.ptr<double>(0), P2.ptr<double>(0),
+                                X.ptr<float>(0)));
+    return X;
+}
+
+/* reference src/mvg.cpp:172-192 */
+Mat triangulate_rectified(const Mat& x1, const Mat& x2, double f, double base, double c1u, double c1v)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    assert(x1.cols == x2.cols);                                                                   /* mvg.cpp:180 */
+    assert(x1.type() == cv::DataType<float>::type && x2.type() == cv::DataType<float>::type);     /* :181-182 */
+    Mat X(3, x1.cols, cv::DataType<float>::type);
+    if (x1.cols > 0)
+        ck(viso_triangulate_rectified_f32(ctx(), x1.ptr<float>(0), x2.ptr<float>(0), x1.cols, f, base, c1u, c1v, X.ptr<float>(0)));
+    return X;
+}
+
+/* reference src/estimation.cpp:29-51 */
+void solveRigidMotion(const Mat& A, const Mat& B, Mat& T)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    assert(A.cols > 1 && A.cols == B.cols && A.rows == B.rows && A.rows == 3); /* BOOST_ASSERT_MSG, estimation.cpp:32-39 */
+    T.create(4, 4, cv::DataType<float>::type);
+    ck(viso_solve_rigid_motion(ctx(), A.ptr<float>(0), B.ptr<float>(0), A.cols, T.ptr<float>(0)));
 }
 
 /* the per-frame loop of reference src/viso.cpp:1167-1330, batched */

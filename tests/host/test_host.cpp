@@ -3,6 +3,8 @@
 // must return true) plus the per-frame loop of sequence_odometry, every result compared with the CPU oracle
 // (oracle/viso_oracle.h -- test infrastructure) on the same inputs.  Needs a GPU; prints "host test OK".
 #include "../../libviso_b200/host/viso.h"
+#include "../../libviso_b200/host/mvg.h"
+#include "../../libviso_b200/host/estimation.h"
 #include "../../include/viso_b200.h"
 #include "../../oracle/viso_oracle.h"
 
@@ -301,8 +303,39 @@ static void test_frame_loop()
     std::printf("final pose z: %g (truth ~ %g)\n", poses.back().at<double>(2, 3), 1.0 * (nF - 1));
 }
 
+// test.cpp:170-206 (solveRigidMotion) and :9-39 (triangulate_dlt), both disabled in the reference
+static void test_mvg_estimation()
+{
+    const float pts[9] = {0, 0, 1, 0, 1, 0, 1, 0, 0}; // columns (0,0,1), (0,1,0), (1,0,0): test.cpp:175-181
+    Mat X1(3, 3, CV_32F), X2(3, 3, CV_32F);
+    const double T1[12] = {1, 0, 0, 1, 0, 0, -1, 2, 0, 1, 0, 3}; // R = Rx(pi/2), t = (1,2,3)
+    for (int c = 0; c < 3; ++c) {
+        for (int r = 0; r < 3; ++r) X1.at<float>(r, c) = pts[3 * c + r];
+        for (int r = 0; r < 3; ++r)
+            X2.at<float>(r, c) = (float)(T1[4 * r] * pts[3 * c] + T1[4 * r + 1] * pts[3 * c + 1] + T1[4 * r + 2] * pts[3 * c + 2] + T1[4 * r + 3]);
+    }
+    Mat T;
+    solveRigidMotion(X2, X1, T); // test.cpp:199
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) REQUIRE(std::fabs(T.at<float>(r, c) - T1[4 * r + c]) < 1e-5);
+
+    Mat P1 = Mat::zeros(3, 4, CV_64F), P2;
+    P1.at<double>(0, 0) = 718.856; P1.at<double>(0, 2) = 607.1928; P1.at<double>(1, 1) = 718.856; P1.at<double>(1, 2) = 185.2157;
+    P1.at<double>(2, 2) = 1;
+    P2 = P1.clone();
+    P2.at<double>(0, 3) = -386.1448;
+    Mat x1(2, 1, CV_32F), x2(2, 1, CV_32F); // X = (0, 0, 1) -> test.cpp:12-33
+    x1.at<float>(0, 0) = (float)P1.at<double>(0, 2); x1.at<float>(1, 0) = (float)P1.at<double>(1, 2);
+    x2.at<float>(0, 0) = (float)(P1.at<double>(0, 2) - 386.1448); x2.at<float>(1, 0) = (float)P1.at<double>(1, 2);
+    Mat Xd = triangulate_dlt(x1, x2, P1, P2);
+    REQUIRE(std::fabs(Xd.at<float>(0, 0)) < 1e-2 && std::fabs(Xd.at<float>(1, 0)) < 1e-2 && std::fabs(Xd.at<float>(2, 0) - 1) < 1e-2);
+    Mat Xr = triangulate_rectified(x1, x2, 718.856, 386.1448 / 718.856, 607.1928, 185.2157);
+    REQUIRE(std::fabs(Xr.at<float>(2, 0) - 1) < 1e-3);
+}
+
 int main()
 {
+    test_mvg_estimation();
     test_nl_rigid_motion1();
     test_frame_loop();
     REQUIRE(viso_b200::kernel_launches() > 0);

@@ -474,3 +474,30 @@ def test_sequence_from_images_and_chunked_ranges(ctx, api, oracle, small_sequenc
     rec2 = seq.download()
     assert rec2.tobytes() == rec.tobytes()
     seq.close()
+
+
+# ------------------------------------------------------------------------------------------------ mvg / estimation
+
+def test_triangulate_dlt_and_solve_rigid_motion(ctx, oracle):
+    """mvg.cpp:124-169 and estimation.cpp:29-51 (test.cpp:9-39, :170-206 recipes).  SVD-based: tolerance, not bits."""
+    from libviso_b200 import synth
+    P1, P2 = synth.kitti_calib()
+    rng = np.random.default_rng(21)
+    X = np.stack([rng.uniform(-20, 20, 500), rng.uniform(-2, 3, 500), rng.uniform(4, 60, 500)])
+    x1 = oracle.project_points(X, P1).astype(np.float32)
+    x2 = oracle.project_points(X, P2).astype(np.float32)
+    got = ctx.triangulate_dlt(x1, x2, P1, P2)
+    want = oracle.triangulate_dlt(x1, x2, P1, P2)
+    assert np.allclose(got, want, rtol=2e-4, atol=1e-4)
+    assert np.allclose(got, X, rtol=2e-2, atol=5e-2)      # test.cpp:36: |X - Xt| < 1e-2-ish at float pixel precision
+    # Kabsch: R = Rx(pi/2), t = (1,2,3) (test.cpp:170-206) and random motions
+    c, s = np.cos(np.pi / 2), np.sin(np.pi / 2)
+    T1 = np.array([[1, 0, 0, 1], [0, c, -s, 2], [0, s, c, 3], [0, 0, 0, 1]])
+    for T_true, n in ((T1, 3), (T1, 200), (oracle.tr2mat([0.1, -0.2, 0.05, 0.5, -1, 2]), 1000)):
+        B = rng.standard_normal((3, n)).astype(np.float32)
+        if n == 3:
+            B = np.array([[0, 0, 1], [0, 1, 0], [1, 0, 0]], np.float32).T.copy()
+        A = (T_true[:3, :3] @ B + T_true[:3, 3:4]).astype(np.float32)
+        T = ctx.solve_rigid_motion(A, B)
+        assert np.abs(T - oracle.solve_rigid_motion(A, B)).max() < 1e-4
+        assert np.abs(T - T_true).max() < 1e-4
