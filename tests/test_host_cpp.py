@@ -37,3 +37,12 @@ def test_host_layer_matches_oracle(tmp_path, api, oracle):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "host test OK" in r.stdout
+
+
+def test_kitti_io_formats(tmp_path):
+    """loadCalib / savePoses (reference src/kitti.cpp:23-64): KITTI calib.txt in, 12-number pose lines out"""
+    exe = str(tmp_path / "test_kitti_io")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", os.path.join(ROOT, "tests", "host", "test_kitti_io.cpp"),
+                           "-o", exe])
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "kitti_io OK" in r.stdout, r.stdout + r.stderr
