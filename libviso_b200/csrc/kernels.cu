@@ -1427,137 +1427,129 @@ __device__ __forceinline__ void sample_from_seeds(const uint32_t* seeds, int N, 
 __constant__ int c_pair_a[27] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 0, 1, 2, 3, 4, 5};
 __constant__ int c_pair_b[27] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 6, 6, 6, 6, 6, 6};
 
-/* One Jacobian row + weighted residual of one point: row r of point_rows() with exactly the same expressions
- * (viso.cpp:1441-1495).  out: 6 Jacobian columns + residual. */
-__device__ __forceinline__ void point_row(const Rot& R, const ParamDev& P, double X1p, double Y1p, double Z1p,
-                                          double weight, double ob_r, int r, double out[7])
-{
-    const double X1c = R.r00 * X1p + R.r01 * Y1p + R.r02 * Z1p + R.tx;
-    const double Y1c = R.r10 * X1p + R.r11 * Y1p + R.r12 * Z1p + R.ty;
-    const double Z1c = R.r20 * X1p + R.r21 * Y1p + R.r22 * Z1p + R.tz;
-    const double X2c = X1c - P.base;
-    const bool xrow = (r == 0 || r == 2);
-    const double num_c = (r == 2) ? X2c : (xrow ? X1c : Y1c); /* the camera coordinate the row differentiates */
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        double X1cd, Y1cd, Z1cd;
-        switch (j) {
-        case 0: X1cd = 0;
-            Y1cd = R.rdrx10 * X1p + R.rdrx11 * Y1p + R.rdrx12 * Z1p;
-            Z1cd = R.rdrx20 * X1p + R.rdrx21 * Y1p + R.rdrx22 * Z1p;
-            break;
-        case 1: X1cd = R.rdry00 * X1p + R.rdry01 * Y1p + R.rdry02 * Z1p;
-            Y1cd = R.rdry10 * X1p + R.rdry11 * Y1p + R.rdry12 * Z1p;
-            Z1cd = R.rdry20 * X1p + R.rdry21 * Y1p + R.rdry22 * Z1p;
-            break;
-        case 2: X1cd = R.rdrz00 * X1p + R.rdrz01 * Y1p;
-            Y1cd = R.rdrz10 * X1p + R.rdrz11 * Y1p;
-            Z1cd = R.rdrz20 * X1p + R.rdrz21 * Y1p;
-            break;
-        case 3: X1cd = 1; Y1cd = 0; Z1cd = 0; break;
-        case 4: X1cd = 0; Y1cd = 1; Z1cd = 0; break;
-        default: X1cd = 0; Y1cd = 0; Z1cd = 1; break;
-        }
-        const double dnum = xrow ? X1cd : Y1cd;
-        out[j] = weight * P.f * (dnum * Z1c - num_c * Z1cd) / (Z1c * Z1c);
-    }
-    const double pred = (r == 2) ? P.f * X2c / Z1c + P.cu : (xrow ? P.f * X1c / Z1c + P.cu : P.f * Y1c / Z1c + P.cv);
-    out[6] = weight * (ob_r - pred);
-}
-
-/* viso.cpp:1406-1424 with the six sin / cos evaluated by six lanes of the warp and broadcast (same values as
- * make_rot: each is one call of the same function on the same argument) */
-__device__ __forceinline__ void make_rot_warp(const double* tr, Rot& R, int lane)
-{
-    double v = 0;
-    if (lane < 6) v = (lane & 1) ? cos(tr[lane >> 1]) : sin(tr[lane >> 1]);
-    const double sx = __shfl_sync(FULL, v, 0), cx = __shfl_sync(FULL, v, 1), sy = __shfl_sync(FULL, v, 2);
-    const double cy = __shfl_sync(FULL, v, 3), sz = __shfl_sync(FULL, v, 4), cz = __shfl_sync(FULL, v, 5);
-    R.tx = tr[3]; R.ty = tr[4]; R.tz = tr[5];
-    R.r00 = +cy * cz;                R.r01 = -cy * sz;                R.r02 = +sy;
-    R.r10 = +sx * sy * cz + cx * sz; R.r11 = -sx * sy * sz + cx * cz; R.r12 = -sx * cy;
-    R.r20 = -cx * sy * cz + sx * sz; R.r21 = +cx * sy * sz + sx * cz; R.r22 = +cx * cy;
-    R.rdrx10 = +cx * sy * cz - sx * sz; R.rdrx11 = -cx * sy * sz - sx * cz; R.rdrx12 = -cx * cy;
-    R.rdrx20 = +sx * sy * cz + cx * sz; R.rdrx21 = -sx * sy * sz + cx * cz; R.rdrx22 = -sx * cy;
-    R.rdry00 = -sy * cz;      R.rdry01 = +sy * sz;      R.rdry02 = +cy;
-    R.rdry10 = +sx * cy * cz; R.rdry11 = -sx * cy * sz; R.rdry12 = +sx * sy;
-    R.rdry20 = -cx * cy * cz; R.rdry21 = +cx * cy * sz; R.rdry22 = -cx * sy;
-    R.rdrz00 = -cy * sz;                R.rdrz01 = -cy * cz;
-    R.rdrz10 = -sx * sy * sz + cx * cz; R.rdrz11 = -sx * sy * cz - cx * sz;
-    R.rdrz20 = +cx * sy * sz + sx * cz; R.rdrz21 = +cx * sy * cz - sx * sz;
-}
+#define VISO_HYP_PER_CTA 32 /* hypotheses per CTA of ransac_hyp_kernel: 4 lanes each */
 
 /*
- * One thread per hypothesis: tr = 0, 3-point sample, Gauss-Newton (minimize_reproj with 3 active points),
- * viso.cpp:1555-1562 + 1583-1623.  Sums run in the reference's row order 0..11.
+ * FOUR LANES per hypothesis: tr = 0, 3-point sample, Gauss-Newton (minimize_reproj with 3 active points),
+ * viso.cpp:1555-1562 + 1583-1623.
+ *
+ * There are only ransac_iter x frame pairs hypotheses (50 k per 1000-frame sequence), each a dependent FP64 chain
+ * of a few thousand instructions per iteration (84 IEEE divisions, six sin / cos, a 6 x 6 LU): one thread per
+ * hypothesis leaves the SMs at ~0.3 IPC.  A quad splits the iteration without changing a single operation:
+ *   lanes 0..2  sin / cos of one angle each (same function, same argument as make_rot), broadcast by shuffle;
+ *   lanes 0..2  the 4 Jacobian rows + residuals of one sample point each (point_rows), written to shared memory;
+ *   lanes 0..3  7 of the 21 + 6 normal-equation sums each, every sum SEQUENTIALLY over rows 0..11 (bit-identical
+ *               to cv::mulTransposed / J^T r);
+ *   lane 0      the LU solve and the convergence test (viso.cpp:1602-1617), broadcast by shuffle.
  */
-__global__ void __launch_bounds__(32) ransac_hyp_kernel(const RansacProb* __restrict__ probs, ParamDev P)
+__global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4) ransac_hyp_kernel(const RansacProb* __restrict__ probs, ParamDev P)
 {
+    __shared__ double rows_s[VISO_HYP_PER_CTA][12][7];
+    __shared__ double sums_s[VISO_HYP_PER_CTA][28];
     const RansacProb& pb = probs[blockIdx.y];
-    const int hId = blockIdx.x * blockDim.x + threadIdx.x;
+    const int hl = threadIdx.x >> 2, q = threadIdx.x & 3, lane = threadIdx.x & 31;
+    const int hId = blockIdx.x * VISO_HYP_PER_CTA + hl;
+    const unsigned qmask = 0xfu << (lane & ~3);
+    const int q0 = lane & ~3; /* first lane of the quad */
     const int n = *pb.n;
-    if (hId >= pb.H || n < pb.min_n || n < 1) return;
+    if (hId >= pb.H || n < pb.min_n || n < 1) return; /* quad uniform */
     int s[3];
     if (pb.table) { s[0] = pb.table[3 * hId]; s[1] = pb.table[3 * hId + 1]; s[2] = pb.table[3 * hId + 2]; }
     else sample_from_seeds(pb.seeds + 3 * hId, n, s);
     const int S = pb.stride;
-    double Xs[3][3], Os[3][4], w[3];
     bool bad_index = false;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        int a = s[i];
-        if (a < 0 || a >= n) { bad_index = true; a = 0; }
+    for (int i = 0; i < 3; ++i)
+        if (s[i] < 0 || s[i] >= n) bad_index = true;
+    /* this lane's sample point (lane 3 mirrors point 2 and does not write) */
+    const int pi = q < 3 ? q : 2;
+    const int a = bad_index ? 0 : s[pi];
+    const double Xp = pb.X[a], Yp = pb.X[S + a], Zp = pb.X[2 * S + a];
+    double ob[4];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) Xs[i][r] = pb.X[r * S + a];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) Os[i][r] = pb.obs[r * S + a];
-        w[i] = weight_of(P, pb.obs[min(i, n - 1)]); /* columns 0,1,2 */
-    }
+    for (int r = 0; r < 4; ++r) ob[r] = pb.obs[r * S + a];
+    const double w = weight_of(P, pb.obs[min(pi, n - 1)]); /* columns 0,1,2: the LOOP index, viso.cpp:1449 */
     double tr[6] = {0, 0, 0, 0, 0, 0};
     int ok = 0;
     if (!bad_index) {
         for (int it = 0; it < 100; ++it) {
+            /* make_rot, viso.cpp:1406-1424: lane 0 -> rx, lane 1 -> ry, lane 2 -> rz */
+            const double ang = tr[q < 3 ? q : 0];
+            const double sv = sin(ang), cv = cos(ang);
             Rot R;
-            make_rot(tr, R, true);
-            double A[6][6], b[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                b[i] = 0;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) A[i][j] = 0;
+            {
+                const double sx = __shfl_sync(qmask, sv, q0), cx = __shfl_sync(qmask, cv, q0);
+                const double sy = __shfl_sync(qmask, sv, q0 + 1), cy = __shfl_sync(qmask, cv, q0 + 1);
+                const double sz = __shfl_sync(qmask, sv, q0 + 2), cz = __shfl_sync(qmask, cv, q0 + 2);
+                R.tx = tr[3]; R.ty = tr[4]; R.tz = tr[5];
+                R.r00 = +cy * cz;                R.r01 = -cy * sz;                R.r02 = +sy;
+                R.r10 = +sx * sy * cz + cx * sz; R.r11 = -sx * sy * sz + cx * cz; R.r12 = -sx * cy;
+                R.r20 = -cx * sy * cz + sx * sz; R.r21 = +cx * sy * sz + sx * cz; R.r22 = +cx * cy;
+                R.rdrx10 = +cx * sy * cz - sx * sz; R.rdrx11 = -cx * sy * sz - sx * cz; R.rdrx12 = -cx * cy;
+                R.rdrx20 = +sx * sy * cz + cx * sz; R.rdrx21 = -sx * sy * sz + cx * cz; R.rdrx22 = -sx * cy;
+                R.rdry00 = -sy * cz;      R.rdry01 = +sy * sz;      R.rdry02 = +cy;
+                R.rdry10 = +sx * cy * cz; R.rdry11 = -sx * cy * sz; R.rdry12 = +sx * sy;
+                R.rdry20 = -cx * cy * cz; R.rdry21 = +cx * cy * sz; R.rdry22 = -cx * sy;
+                R.rdrz00 = -cy * sz;                R.rdrz01 = -cy * cz;
+                R.rdrz10 = -sx * sy * sz + cx * cz; R.rdrz11 = -sx * sy * cz - cx * sz;
+                R.rdrz20 = +cx * sy * sz + sx * cz; R.rdrz21 = +cx * sy * cz - sx * sz;
             }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            if (q < 3) {
                 double rows[4][7];
-                point_rows(R, P, Xs[i][0], Xs[i][1], Xs[i][2], w[i], Os[i], rows);
+                point_rows(R, P, Xp, Yp, Zp, w, ob, rows);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int a = 0; a < 6; ++a) {
+                    for (int c = 0; c < 7; ++c) rows_s[hl][4 * q + r][c] = rows[r][c];
+            }
+            __syncwarp(qmask);
 #pragma unroll
-                        for (int c = a; c < 6; ++c) A[a][c] += rows[r][a] * rows[r][c];
-                        b[a] += rows[r][a] * rows[r][6];
-                    }
+            for (int j = 0; j < 7; ++j) {
+                const int t = q + 4 * j;
+                if (t < 27) {
+                    const int sa = c_pair_a[t], sb = c_pair_b[t];
+                    double acc = 0;
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) acc += rows_s[hl][k][sa] * rows_s[hl][k][sb];
+                    sums_s[hl][t] = acc;
                 }
             }
+            __syncwarp(qmask);
+            int flag = 0; /* 0 continue, 1 converged, 2 singular */
+            double p[6] = {0, 0, 0, 0, 0, 0};
+            if (q == 0) {
+                double A[6][6], b[6];
+                int t = 0;
 #pragma unroll
-            for (int a = 0; a < 6; ++a)
+                for (int r = 0; r < 6; ++r)
 #pragma unroll
-                for (int c = 0; c < a; ++c) A[a][c] = A[c][a];
-            if (!lu_solve6(A, b)) { ok = 0; break; }
-            bool conv = true;
+                    for (int c = r; c < 6; ++c) { A[r][c] = sums_s[hl][t]; A[c][r] = sums_s[hl][t]; ++t; }
 #pragma unroll
-            for (int j = 0; j < 6; ++j)
-                if (b[j] > P.thresh) { conv = false; break; } /* fabs(p > thresh), viso.cpp:1610 */
-            if (conv) { ok = 1; break; }
+                for (int r = 0; r < 6; ++r) b[r] = sums_s[hl][21 + r];
+                if (!lu_solve6(A, b)) flag = 2;
+                else {
+                    flag = 1;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) tr[j] = tr[j] + b[j];
+                    for (int j = 0; j < 6; ++j)
+                        if (b[j] > P.thresh) flag = 0; /* fabs(p > thresh), viso.cpp:1610 */
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) p[j] = b[j];
+                }
+            }
+            flag = __shfl_sync(qmask, flag, q0);
+            if (flag == 2) { ok = 0; break; }
+            if (flag == 1) { ok = 1; break; }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) tr[j] = tr[j] + __shfl_sync(qmask, p[j], q0);
+            __syncwarp(qmask); /* rows_s / sums_s are rewritten by the next iteration */
         }
     }
+    if (q == 0) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) pb.hyp_tr[6 * hId + j] = tr[j];
-    pb.hyp_ok[hId] = ok;
-    pb.hyp_count[hId] = -1;
+        for (int j = 0; j < 6; ++j) pb.hyp_tr[6 * hId + j] = tr[j];
+        pb.hyp_ok[hId] = ok;
+        pb.hyp_count[hId] = -1;
+    }
 }
 
 /* One warp per hypothesis: support-set size, viso.cpp:1563 (get_inliers, :1509-1537) */
@@ -2126,7 +2118,7 @@ cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, 
                                int* launches)
 {
     if (n_probs <= 0 || max_H <= 0) return cudaSuccess;
-    ransac_hyp_kernel<<<dim3((max_H + 31) / 32, n_probs), 32, 0, s>>>(probs, p);
+    ransac_hyp_kernel<<<dim3((max_H + VISO_HYP_PER_CTA - 1) / VISO_HYP_PER_CTA, n_probs), VISO_HYP_PER_CTA * 4, 0, s>>>(probs, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ransac_score_kernel<<<dim3((max_H + 7) / 8, n_probs), 256, 0, s>>>(probs, p);
