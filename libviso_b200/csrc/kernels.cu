@@ -752,11 +752,14 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
  * none).
  */
 __global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, VISO_MATCH_MINB)
-sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, int reg_cap, unsigned long long* sad_pairs,
-                 int* n_pending)
+sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, int reg_cap, int ql_cap,
+                 unsigned long long* sad_pairs, int* n_pending)
 {
     extern __shared__ uint4 reg[];                                /* staged neighbourhood, reg_cap records */
-    __shared__ unsigned short qlist[32][VISO_QLIST_CAP + 2];      /* +2: odd word stride, lanes = queries write */
+    /* per-query candidate lists (region indices), 32 x (ql_cap + 2): the +2 makes the word stride odd so that
+     * lanes = queries write without bank conflicts */
+    unsigned short* const qlist = reinterpret_cast<unsigned short*>(reg + reg_cap);
+    const int ql_stride = ql_cap + 2;
     __shared__ int qcnt[32];
     __shared__ int row_off[VISO_MAX_REG_ROWS + 1];
     __shared__ int tile_s[4];
@@ -880,7 +883,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                     const float dist = l1_dist(qx, qy, p.x, p.y);
                     if (act && dist <= r && dist < D0) {
                         const int j = atomicAdd(&qcnt[lane], 1);
-                        if (j < VISO_QLIST_CAP) qlist[lane][j] = (unsigned short)i;
+                        if (j < ql_cap) qlist[lane * ql_stride + j] = (unsigned short)i;
                     }
                 }
             }
@@ -889,7 +892,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
             for (int kk = warp; kk < gq; kk += VISO_MATCH_WARPS) {
                 const uint4 qrec = qrec_s[kk];
                 const int n = qcnt[kk];
-                if (n > VISO_QLIST_CAP || n > P.K) { /* top-K cut or list overflow: left to the generic kernel */
+                if (n > ql_cap || n > P.K) { /* top-K cut or list overflow: left to the generic kernel */
                     if (lane == 0) {
                         job.out[qrec.z] = make_int4(0, 0, 0, VISO_PENDING);
                         atomicAdd(n_pending, 1);
@@ -902,7 +905,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 const uint4 qa = __ldg(qp), qb = __ldg(qp + 8);
                 BestState st;
                 st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
-                unsigned short* ql = qlist[kk];
+                unsigned short* ql = qlist + kk * ql_stride;
                 int nlist = n;
                 if (P.epipolar) { /* Sampson gate (viso.cpp:695-701), lanes = candidates, compacting the list in place */
                     nlist = 0;
@@ -2073,17 +2076,22 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
     if (!(expect >= 0)) expect = 0;
     int cap = (int)fmin(6144.0, fmax(256.0, 2.0 * expect + 64.0));
     cap = (cap + 63) & ~63;
-    const size_t smem = (size_t)cap * sizeof(uint4);
+    /* per-query list capacity: twice the expected number of points in the L1 diamond (2 r^2), 64..256 */
+    const double in_diamond = (double)max_nt * fmin(1.0, 2.0 * (double)r * r / (ext_x * ext_y));
+    int ql_cap = (int)fmin(256.0, fmax(64.0, 2.0 * in_diamond + 16.0));
+    ql_cap = (ql_cap + 31) & ~31;
+    const size_t smem = (size_t)cap * sizeof(uint4) + (size_t)32 * (ql_cap + 2) * sizeof(unsigned short);
     static int attr_set = 0;
     if (smem > 24 * 1024 && !attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 16);
+        cudaError_t e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             6144 * 16 + 32 * 258 * 2);
         if (e != cudaSuccess) return e;
         attr_set = 1;
     }
     cudaError_t e = cudaMemsetAsync(n_pending, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     const int tiles = ((g.gx + VISO_TILE_W - 1) / VISO_TILE_W) * ((g.gy + VISO_TILE_H - 1) / VISO_TILE_H);
-    sad_match_kernel<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, sad_pairs, n_pending);
+    sad_match_kernel<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, ql_cap, sad_pairs, n_pending);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, n_pending, 1);

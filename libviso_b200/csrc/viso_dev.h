@@ -32,7 +32,6 @@
 #endif
 #define VISO_TILE_W 6            /* query tile of sad_match: 6 x 4 cells = 96 x 64 px */
 #define VISO_TILE_H 4
-#define VISO_QLIST_CAP 128       /* per-query candidate list of the tile path (region indices) */
 #define VISO_STRIP_QPC 16         /* queries per CTA of the generic match kernel */
 #define VISO_PENDING (-2)         /* dense result .w: left by the tile kernel for the generic kernel */
 #define VISO_MAX_REG_ROWS 64     /* grid rows a staged tile neighbourhood may span */
