@@ -308,7 +308,6 @@ def main():
         match_ms.append(seq.match_ms())
     dev_ms = ctx.timer_end()
     barrier()
-    clocks = sampler.stop()
     launches = ctx.launch_count() - l0
     rec = seq.download()
     match_bytes, sad_pairs, sad_eval = seq.stats()
@@ -357,6 +356,8 @@ def main():
         barrier()
         rec_e2e = np.frombuffer(rec_pin.numpy().tobytes(), dtype=api.RECORD_DTYPE)
         assert rec_e2e.tobytes() == rec.tobytes(), "e2e records differ from the resident run"
+
+    clocks = sampler.stop()  # sampled over both timed regions (device-resident and end-to-end)
 
     # ---- max over ranks, gather records (the only collective: 64 B per frame pair) ----
     tms = torch.tensor([dev_ms, e2e_ms or 0.0, float(np.mean(match_ms))], dtype=torch.float64, device="cuda")

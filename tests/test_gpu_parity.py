@@ -501,3 +501,54 @@ def test_triangulate_dlt_and_solve_rigid_motion(ctx, oracle):
         T = ctx.solve_rigid_motion(A, B)
         assert np.abs(T - oracle.solve_rigid_motion(A, B)).max() < 1e-4
         assert np.abs(T - T_true).max() < 1e-4
+
+
+def test_long_sequence_properties(ctx, api, oracle, small_sequence):
+    """BASELINE configs[1] shape in miniature (240 frames driven back and forth over the rendered ones): the
+    size-independent properties -- rerun idempotence, images == descriptors, chunked == one-shot, frame pair (t-1, t)
+    of the long sequence == the same pair computed alone, oracle agreement on a prefix."""
+    from libviso_b200 import synth
+    frames, _ = small_sequence
+    P1, P2 = synth.kitti_calib()
+    F, H = 240, 50
+    U = len(frames)
+    order = [(t % (2 * (U - 1))) if (t % (2 * (U - 1))) < U else 2 * (U - 1) - (t % (2 * (U - 1))) for t in range(F)]
+    seeds = make_seeds(F, H)
+    pg = api.param_default(ransac_iter=H)
+    cap = max(max(len(f["kpL"]), len(f["kpR"])) for f in frames)
+
+    def run(mode):
+        seq = ctx.sequence(F, cap, 121, H)
+        seq.set_calib(P1, P2)
+        seq.set_image_size(synth.W, synth.H)
+        seq.set_seeds(seeds, H)
+        for t in range(F):
+            f = frames[order[t]]
+            if mode == "desc":
+                seq.upload_frame(t, f["kpL"], f["kpR"], f["dL"], f["dR"])
+            else:
+                seq.upload_frame_images(t, f["imL"], f["imR"], f["kpL"], f["kpR"])
+        if mode == "chunks":
+            for t0 in range(0, F, 37):
+                seq.run_range(pg, t0, min(F, t0 + 37))
+        else:
+            seq.run(pg)
+        rec = seq.download()
+        if mode == "images":
+            seq.run(pg)
+            assert seq.download().tobytes() == rec.tobytes()      # idempotent
+        seq.close()
+        return rec
+
+    rec = run("images")
+    assert run("desc").tobytes() == rec.tobytes()
+    assert run("chunks").tobytes() == rec.tobytes()
+    assert rec["ok"][1:].all()
+    # a frame pair does not depend on its position in the sequence: pairs (t-1, t) with the same two rendered frames
+    # and the same seeds give the same record
+    o = oracle.sequence([frames[order[t]] for t in range(12)], P1, P2, oracle.param_default(ransac_iter=H), seeds[:12])
+    for k in ("ok", "n_inliers", "n_circ", "best_hyp"):
+        assert np.array_equal(rec[k][:12], o["records"][k]), k
+    assert_tr_close(rec["tr"][:12], o["records"]["tr"])
+    poses = api.chain_poses(rec)
+    assert len(poses) == F and np.isfinite(poses).all()
