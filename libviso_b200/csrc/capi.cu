@@ -1,7 +1,7 @@
 /*
  * capi.cu -- the C-ABI of include/viso_b200.h: context, buffer management, job tables and launches.
  *
- * Host side only; every numeric result on the hot path is produced by the kernels in kernels.cu.  There is no
+ * Host side only; every numeric result on the hot path is produced by the kernels in match.cu, sort_circle.cu, estimation.cu and geometry.cu.  There is no
  * CPU fallback: without a CUDA device viso_create() fails.  The only arithmetic done here is the once-per-sequence /
  * per-pose host bookkeeping the reference also keeps outside the per-frame loop (F_from_P, tr2mat, pose chaining)
  * and the RANSAC sample-table generators.

@@ -1,0 +1,990 @@
+/*
+ * match.cu -- descriptor packing / extraction, candidate grid and the SAD matching kernels (match_desc,
+ * viso.cpp:668-722; MyFeatureExtractor, viso.cpp:1004-1024) with their launch wrappers.
+ */
+#include "viso_dev.h"
+#include "common.cuh"
+
+#include <stdlib.h>
+#include <algorithm>
+
+/* ------------------------------------------------------------------------------------------------ pack */
+
+/*
+ * f32 cv::Mat descriptor rows (viso.cpp:999-1002) -> biased u16 rows (v + 1024, pad elements 0), plus the u32 sum
+ * of the packed row.  One warp per row, lane l owns elements 4l..4l+3.  Also the domain check (integer valued,
+ * |v| <= 1023).
+ */
+__global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restrict__ jobs, int dlen, int* err)
+{
+    const PackJob job = jobs[blockIdx.y];
+    if (job.from_image && *job.from_image) return;
+    const int n = *job.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * 8 + warp; row < n; row += gridDim.x * 8) {
+        const float* src = job.d + (size_t)row * dlen;
+        unsigned u[4];
+        unsigned sum = 0;
+        int bad = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int k = lane * 4 + e;
+            unsigned v = 0;
+            if (k < dlen) {
+                float f = __ldg(src + k);
+                float r = truncf(f);
+                if (!(f == r) || !(fabsf(f) <= 1023.f)) bad = 1;
+                else v = (unsigned)((int)r + 1024);
+            }
+            u[e] = v;
+            sum += v;
+        }
+        uint2 w;
+        w.x = u[0] | (u[1] << 16);
+        w.y = u[2] | (u[3] << 16);
+        reinterpret_cast<uint2*>(job.out + (size_t)row * VISO_DESC_U16)[lane] = w;
+        const unsigned tot = warp_sum_u(sum);
+        if (lane == 0) job.rsum[row] = tot;
+        if (bad) atomicOr(err, 1);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ extract */
+
+/*
+ * MyFeatureExtractor::computeImpl, viso.cpp:1004-1024, fused with the packing above: for keypoint k with
+ * p = Point2i(kp.pt) (cv::saturate_cast = round half to even, :1013), element (i, j), i, j in [-R, R] row-major, is
+ *     (p.y+i > 0 && p.y+i < rows && p.x+j > 0 && p.x+j < cols) ? sobel_x(p.y+i, p.x+j) : 0        (:1018)
+ * with sobel_x = cv::Sobel(image, CV_32F, 1, 0, 3, 1, 0, BORDER_REFLECT_101) (:1010), i.e. the integer
+ *     (I(y-1,x+1) + 2 I(y,x+1) + I(y+1,x+1)) - (I(y-1,x-1) + 2 I(y,x-1) + I(y+1,x-1)),  index -1 -> 1, n -> n-2.
+ * Values are integers in [-1020, 1020]; the row is written biased (+1024) in the u16 layout with its sum.
+ * One warp per keypoint.  The (2R+3)^2 source window is first staged in shared memory with the reflection already
+ * applied (6 byte loads per lane, ~3 image rows per load instruction instead of 11), then lane l computes elements
+ * 4l..4l+3 from the staged window.
+ */
+#define VISO_EXTRACT_WIN 16 /* staged window pitch; supports radius <= 6 (2R+3 <= 15) */
+
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return min(max(i, 0), n - 1); /* far outside: any in-range pixel, the sample is masked to 0 anyway */
+}
+
+#define VISO_EXTRACT_KPW 4 /* keypoints per warp iteration: their image loads are all in flight together */
+
+template <int radius>
+__global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __restrict__ jobs, int width, int height, int pitch)
+{
+    __shared__ unsigned char win_s[8][VISO_EXTRACT_KPW][VISO_EXTRACT_WIN * VISO_EXTRACT_WIN];
+    const ExtractJob job = jobs[blockIdx.y];
+    if (!*job.from_image) return;
+    const int n = *job.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int side = 2 * radius + 1, dlen = side * side, wside = side + 2, wn = wside * wside;
+    constexpr int NL = (wn + 31) / 32;
+    for (int row0 = (blockIdx.x * 8 + warp) * VISO_EXTRACT_KPW; row0 < n; row0 += gridDim.x * 8 * VISO_EXTRACT_KPW) {
+        int px[VISO_EXTRACT_KPW], py[VISO_EXTRACT_KPW];
+        unsigned char pix[VISO_EXTRACT_KPW][NL];
+        /* the image is touched once per frame, so these loads mostly miss to DRAM: issue all of them first */
+#pragma unroll
+        for (int q = 0; q < VISO_EXTRACT_KPW; ++q) {
+            const float2 kp = job.kp[min(row0 + q, n - 1)];
+            px[q] = __float2int_rn(kp.x); py[q] = __float2int_rn(kp.y);
+#pragma unroll
+            for (int j = 0; j < NL; ++j) {
+                const int idx = min(lane + 32 * j, wn - 1);
+                const int wy = idx / wside, wx = idx - wy * wside;
+                const int iy = reflect101(py[q] - radius - 1 + wy, height), ix = reflect101(px[q] - radius - 1 + wx, width);
+                pix[q][j] = __ldg(job.img + (size_t)iy * pitch + ix);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < VISO_EXTRACT_KPW; ++q)
+#pragma unroll
+            for (int j = 0; j < NL; ++j) {
+                const int idx = lane + 32 * j;
+                if (idx < wn) {
+                    const int wy = idx / wside, wx = idx - wy * wside;
+                    win_s[warp][q][wy * VISO_EXTRACT_WIN + wx] = pix[q][j];
+                }
+            }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < VISO_EXTRACT_KPW; ++q) {
+            const int row = row0 + q;
+            if (row >= n) break; /* warp uniform */
+            const unsigned char* win = win_s[warp][q];
+            unsigned u[4];
+            unsigned sum = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = lane * 4 + e;
+                unsigned v = 0;
+                if (k < dlen) {
+                    const int r = k / side, c = k - r * side;
+                    const int y = py[q] + r - radius, x = px[q] + c - radius;
+                    int sob = 0;
+                    if (y > 0 && y < height && x > 0 && x < width) {
+                        const unsigned char* w0 = win + r * VISO_EXTRACT_WIN + c; /* window row r = image row y-1 */
+                        sob = ((int)w0[2] + 2 * (int)w0[VISO_EXTRACT_WIN + 2] + (int)w0[2 * VISO_EXTRACT_WIN + 2]) -
+                              ((int)w0[0] + 2 * (int)w0[VISO_EXTRACT_WIN] + (int)w0[2 * VISO_EXTRACT_WIN]);
+                    }
+                    v = (unsigned)(sob + 1024);
+                }
+                u[e] = v;
+                sum += v;
+            }
+            uint2 w;
+            w.x = u[0] | (u[1] << 16);
+            w.y = u[2] | (u[3] << 16);
+            reinterpret_cast<uint2*>(job.out + (size_t)row * VISO_DESC_U16)[lane] = w;
+            const unsigned tot = warp_sum_u(sum);
+            if (lane == 0) job.rsum[row] = tot;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ grid */
+
+/*
+ * Counting sort of one keypoint set into 16-px cells (one CTA per set).  Emits, in cell order, the candidate
+ * records the matcher streams: srec = (x, y, original index, row sum).
+ */
+__global__ void __launch_bounds__(512) grid_build_kernel(const GridJob* __restrict__ jobs, GridCfg g)
+{
+    extern __shared__ int sm[];
+    const int ncell = g.gx * g.gy;
+    int* hist = sm;               /* ncell + 1 */
+    int* cursor = sm + ncell + 1; /* ncell */
+    const GridJob job = jobs[blockIdx.x];
+    const int n = *job.n;
+    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) hist[c] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float2 p = job.xy[i];
+        atomicAdd(&hist[cell_coord(p.y, g.gy) * g.gx + cell_coord(p.x, g.gx)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) { /* exclusive scan: each lane owns a contiguous chunk */
+        const int lane = threadIdx.x;
+        const int chunk = (ncell + 31) / 32;
+        const int b = lane * chunk, e = min(b + chunk, ncell);
+        int s = 0;
+        for (int c = b; c < e; ++c) s += hist[c];
+        int incl = warp_incl_scan(s, lane);
+        int run = incl - s;
+        for (int c = b; c < e; ++c) { int h = hist[c]; hist[c] = run; run += h; }
+        if (lane == 31) hist[ncell] = incl;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) {
+        int v = hist[c];
+        job.cell_start[c] = v;
+        if (c < ncell) cursor[c] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float2 p = job.xy[i];
+        int pos = atomicAdd(&cursor[cell_coord(p.y, g.gy) * g.gx + cell_coord(p.x, g.gx)], 1);
+        job.srec[pos] = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), (unsigned)i, job.rsum[i]);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ match */
+
+/* sampsonDistance + algebricDistance, viso.cpp:652-666, 390-407: literal operation order (no FMA) */
+__device__ __forceinline__ double sampson_dev(const double* F, float p1x, float p1y, float p2x, float p2y)
+{
+    double Fx0 = F[0] * p1x + F[1] * p1y + F[2];
+    double Fx1 = F[3] * p1x + F[4] * p1y + F[5];
+    double Ftx0 = F[0] * p2x + F[3] * p2y + F[6];
+    double Ftx1 = F[1] * p2x + F[4] * p2y + F[7];
+    float a0 = p1x, a1 = p1y, a2 = 1.f, b0 = p2x, b1 = p2y, b2 = 1.f;
+    double alg = b0 * F[0] * a0 + b0 * F[1] * a1 + b0 * F[2] * a2 +
+                 b1 * F[3] * a0 + b1 * F[4] * a1 + b1 * F[5] * a2 +
+                 b2 * F[6] * a0 + b2 * F[7] * a1 + b2 * F[8] * a2;
+    float ad = (float)alg;
+    float ad2 = __fmul_rn(ad, ad);
+    return (double)ad2 / (Fx0 * Fx0 + Fx1 * Fx1 + Ftx0 * Ftx0 + Ftx1 * Ftx1);
+}
+
+__device__ __forceinline__ float l1_dist(float qx, float qy, float tx, float ty)
+{
+    return __fadd_rn(fabsf(__fsub_rn(tx, qx)), fabsf(__fsub_rn(ty, qy)));
+}
+
+__device__ __forceinline__ bool key_greater(float d1, int i1, float d2, int i2)
+{
+    return d1 > d2 || (d1 == d2 && i1 > i2);
+}
+
+/* per-warp shared scratch.  The top-K threshold search (hist / tie arrays) and the scanned-candidate list are never
+ * live at the same time, so they share storage. */
+struct WarpScratch {
+    int rowS0[32];
+    int rowPre[33];
+    int pad_[3];
+    union {
+        uint4 list[VISO_LIST_CAP];             /* (target index, L1 distance bits, row sum, -) */
+        struct {
+            unsigned hist[VISO_HIST_BINS];
+            float tieD[VISO_TIE_CAP];
+            int tieI[VISO_TIE_CAP];
+        } sel;
+    };
+};
+
+struct QueryGeom {
+    float qx, qy, r, slack;
+    int cy0, cy1;
+};
+
+__device__ __forceinline__ float geom_slack(float qx, float qy, float r)
+{
+    return 1.0f + 4e-6f * (fabsf(qx) + fabsf(qy) + r);
+}
+
+__device__ __forceinline__ QueryGeom make_geom(GridCfg g, float qx, float qy, float r)
+{
+    QueryGeom q;
+    q.qx = qx; q.qy = qy; q.r = r;
+    q.slack = geom_slack(qx, qy, r);
+    q.cy0 = cell_coord(qy - r - q.slack, g.gy);
+    q.cy1 = cell_coord(qy + r + q.slack, g.gy);
+    return q;
+}
+
+/* ---- candidate visitors: f(in, dist, rec) is called by all lanes of the warp, 32 points per call;
+ *      rec = (x, y, original index, row sum) of this lane's point, dist its L1 distance to the query ---- */
+
+/* Generic visitor: walks the spans of the target grid rows under the L1 diamond straight from global memory.
+ * Handles any radius / point count. */
+struct GlobalVisitor {
+    const SetView& t;
+    GridCfg g;
+    QueryGeom q;
+    WarpScratch& ws;
+    int lane;
+    int total0;
+    bool one_group;
+
+    /* Spans of the (up to 32) grid rows rg..rg+31 that overlap the diamond: lane l owns row rg+l.  Leaves the
+     * flattened prefix table in ws and returns the number of points in those spans (same value in all lanes). */
+    __device__ __forceinline__ int setup_rows(int rg)
+    {
+        const int cy = rg + lane;
+        int s0 = 0, len = 0;
+        if (cy <= q.cy1) {
+            const float lo = (cy == 0) ? -CUDART_INF_F : (float)(cy * VISO_GRID_CS);
+            const float hi = (cy == g.gy - 1) ? CUDART_INF_F : (float)((cy + 1) * VISO_GRID_CS);
+            const float dymin = fmaxf(0.f, fmaxf(lo - q.qy, q.qy - hi));
+            const float rem = q.r - dymin + q.slack;
+            if (rem >= 0.f) {
+                const int cx0 = cell_coord(q.qx - rem, g.gx), cx1 = cell_coord(q.qx + rem, g.gx);
+                s0 = __ldg(t.cell_start + cy * g.gx + cx0);
+                len = __ldg(t.cell_start + cy * g.gx + cx1 + 1) - s0;
+            }
+        }
+        const int incl = warp_incl_scan(len, lane);
+        __syncwarp();
+        ws.rowS0[lane] = s0;
+        ws.rowPre[lane] = incl - len;
+        if (lane == 31) ws.rowPre[32] = incl;
+        __syncwarp();
+        return __shfl_sync(FULL, incl, 31);
+    }
+
+    /* upper bound on the in-radius count: the number of points in the visited spans */
+    __device__ __forceinline__ int bound()
+    {
+        one_group = q.cy1 - q.cy0 < 32;
+        total0 = setup_rows(q.cy0);
+        int b = total0;
+        if (!one_group)
+            for (int rg = q.cy0 + 32; rg <= q.cy1; rg += 32) b += setup_rows(rg);
+        return b;
+    }
+
+    template <class Fn> __device__ __forceinline__ void rows(int total, Fn&& f)
+    {
+        int row = 0;
+        for (int base = 0; base < total; base += 32) {
+            const int fl = base + lane;
+            const bool in = fl < total;
+            float dist = CUDART_INF_F;
+            uint4 rec = make_uint4(0, 0, 0xffffffffu, 0);
+            if (in) {
+                while (fl >= ws.rowPre[row + 1]) ++row;
+                const int p = ws.rowS0[row] + (fl - ws.rowPre[row]);
+                rec = __ldg(t.srec + p);
+                dist = l1_dist(q.qx, q.qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
+            }
+            f(in, dist, rec);
+        }
+    }
+
+    template <class Fn> __device__ __forceinline__ void all(Fn&& f)
+    {
+        if (one_group) { rows(total0, f); return; } /* the row table of the only group is still in place */
+        for (int rg = q.cy0; rg <= q.cy1; rg += 32) {
+            const int total = setup_rows(rg);
+            rows(total, f);
+        }
+    }
+};
+
+__device__ __forceinline__ int dist_bin(float dist, float scale)
+{
+    return min(VISO_HIST_BINS - 1, (int)(dist * scale));
+}
+
+/* running result of one query (warp-uniform values) */
+struct BestState {
+    unsigned b1, b2;     /* smallest / second smallest SAD with multiplicity; 0xffffffff = none */
+    unsigned bdist;      /* float bits of the L1 distance of the best (>= +0, so unsigned order == float order) */
+    int bidx;
+};
+
+/*
+ * Phase 2: exact SAD of the n listed candidates against the query, 32 candidates per batch.
+ *
+ * Eight lanes share one 256-byte descriptor row: lane `sub` of the group reads the 16-byte chunks sub and 8 + sub,
+ * so each of the two LDG.128 of a step covers exactly one full 128-byte line per row (4 rows = 4 lines per
+ * instruction, no partially used sector); four rows per step, eight steps per batch.  Each lane holds the matching
+ * two chunks of the query row in registers (qa, qb).  Per element pair one VIMNMX.U16x2 + one
+ * add:  sum|a-b| = sum(a) + sum(b) - 2*sum(min(a,b)), with the row sums precomputed by the pack kernel.  The
+ * eight per-step partial sums of a lane are then transposed-reduced across the 8 lanes of a row group (7 SHFL), so
+ * that lane (g, sub) ends up with the complete sum for candidate 4*sub + g of the batch, and the batch is folded
+ * into the running (best, second best) with REDUX min/max -- ties on the SAD go to the largest (L1, index) key,
+ * i.e. the last one in the reference's scan order (viso.cpp:703).
+ */
+/* one batch of NS*4 candidates starting at list entry `base` (NS = 8: up to 32, NS = 4: up to 16).  Branch free:
+ * entries past the end of the list are clamped to the last one (a repeated L1-hit load) and masked afterwards, so
+ * that all 2*NS row loads of the batch can be in flight together. */
+/* where the candidates of a query come from: target index of entry e, and (index, L1 distance bits, row sum) */
+struct ListAcc { /* the warp's uint4 list (generic kernel) */
+    const WarpScratch& ws;
+    __device__ __forceinline__ unsigned index(int e) const { return ws.list[e].x; }
+    __device__ __forceinline__ uint4 entry(int e) const { return ws.list[e]; }
+};
+struct TileAcc { /* region indices into the staged neighbourhood (tile kernel): the distance is recomputed */
+    const unsigned short* ql;
+    const uint4* reg;
+    float qx, qy;
+    __device__ __forceinline__ unsigned index(int e) const { return reg[ql[e]].z; }
+    __device__ __forceinline__ uint4 entry(int e) const
+    {
+        const uint4 r = reg[ql[e]];
+        return make_uint4(r.z, __float_as_uint(l1_dist(qx, qy, __uint_as_float(r.x), __uint_as_float(r.y))), r.w, 0u);
+    }
+};
+
+/* NB = butterfly width in steps (8: up to 32 candidates, 4: up to 16), NL <= NB = steps whose rows are actually
+ * loaded and evaluated (the rest contribute 0 and are masked) */
+template <int NB, int NL, class Acc>
+__device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, const Acc& acc_, int base, int n, int lane,
+                                           const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
+{
+    const int sub = lane & 7, g = lane >> 3;
+    const bool b0 = sub & 1, b1 = sub & 2, b2 = sub & 4;
+    /* lane L fetches the record of candidate base + L once; the steps and the final fold get it by shuffle */
+    const uint4 ent = acc_.entry(min(base + lane, n - 1));
+    unsigned part[NB];
+#pragma unroll
+    for (int s = 0; s < NB; ++s) part[s] = 0;
+#pragma unroll
+    for (int h = 0; h < NL; h += VISO_EVAL_DEPTH) { /* VISO_EVAL_DEPTH steps = 2*VISO_EVAL_DEPTH row loads in flight */
+        uint4 ra[VISO_EVAL_DEPTH], rb[VISO_EVAL_DEPTH];
+#pragma unroll
+        for (int s = 0; s < VISO_EVAL_DEPTH; ++s) {
+            if (h + s < NL) {
+                const unsigned idx = __shfl_sync(FULL, ent.x, 4 * (h + s) + g);
+                const uint4* rp = tbase + (size_t)idx * (VISO_DESC_U16 / 8);
+                ra[s] = __ldg(rp);
+                rb[s] = __ldg(rp + 8);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < VISO_EVAL_DEPTH; ++s) {
+            if (h + s < NL) {
+                const unsigned acc = __vminu2(qa.x, ra[s].x) + __vminu2(qa.y, ra[s].y) + __vminu2(qa.z, ra[s].z) + __vminu2(qa.w, ra[s].w) +
+                                     __vminu2(qb.x, rb[s].x) + __vminu2(qb.y, rb[s].y) + __vminu2(qb.z, rb[s].z) + __vminu2(qb.w, rb[s].w);
+                part[h + s] = (acc & 0xffffu) + (acc >> 16); /* 16 elements x 2047 < 65536: no carry between halves */
+            }
+        }
+    }
+    /* transposed reduction over the 8 lanes of a row group: lane (g, sub) ends with candidate 4*step + g where
+     * step = sub (NB = 8) or sub & 3 (NB = 4; lanes sub and sub^4 then hold the same candidate) */
+    unsigned r2[2];
+    if (NB == 8) {
+        unsigned r4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned lo = part[2 * j], hi = part[2 * j + 1];
+            r4[j] = (b0 ? hi : lo) + __shfl_xor_sync(FULL, b0 ? lo : hi, 1);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const unsigned lo = r4[2 * j], hi = r4[2 * j + 1];
+            r2[j] = (b1 ? hi : lo) + __shfl_xor_sync(FULL, b1 ? lo : hi, 2);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const unsigned lo = part[2 * j], hi = part[2 * j + 1];
+            r2[j] = (b0 ? hi : lo) + __shfl_xor_sync(FULL, b0 ? lo : hi, 1);
+        }
+    }
+    unsigned tot;
+    int slot; /* position of this lane's candidate inside the batch */
+    bool mine = true;
+    if (NB == 8) {
+        tot = (b2 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b2 ? r2[0] : r2[1], 4);
+        slot = 4 * sub + g;
+    } else {
+        const unsigned t2 = (b1 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b1 ? r2[0] : r2[1], 2);
+        tot = t2 + __shfl_xor_sync(FULL, t2, 4);
+        slot = 4 * (sub & 3) + g;
+        mine = !b2; /* the duplicate lanes sit out */
+    }
+    const unsigned cidx = __shfl_sync(FULL, ent.x, slot), cdist = __shfl_sync(FULL, ent.y, slot);
+    const unsigned csum = __shfl_sync(FULL, ent.z, slot);
+    unsigned sad = 0xffffffffu, dbits = 0;
+    int idx = -1;
+    if (mine && base + slot < n) {
+        sad = qsum + csum - 2u * tot;
+        dbits = cdist;
+        idx = (int)cidx;
+    }
+    const unsigned m1 = __reduce_min_sync(FULL, sad);
+    const unsigned ties = __ballot_sync(FULL, sad == m1);
+    unsigned m2 = m1;
+    if (__popc(ties) < 2) m2 = __reduce_min_sync(FULL, sad == m1 ? 0xffffffffu : sad);
+    const unsigned kd = __reduce_max_sync(FULL, sad == m1 ? dbits : 0u);
+    const int ki = __reduce_max_sync(FULL, (sad == m1 && dbits == kd) ? idx : -1);
+    if (m1 < st.b1) {
+        st.b2 = min(st.b1, m2); st.b1 = m1; st.bdist = kd; st.bidx = ki;
+    } else if (m1 == st.b1) {
+        st.b2 = st.b1;
+        if (kd > st.bdist || (kd == st.bdist && ki > st.bidx)) { st.bdist = kd; st.bidx = ki; }
+    } else if (m1 < st.b2) {
+        st.b2 = m1;
+    }
+}
+
+template <class Acc>
+__device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, const Acc& acc, int n, int lane,
+                                          const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
+{
+    const uint4* tbase = reinterpret_cast<const uint4*>(tdesc) + (lane & 7);
+    int base = 0;
+    for (; n - base > 24; base += 32) eval_batch<8, 8>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+    const int rest = n - base; /* 0..24: rows are loaded in units of 8 candidates */
+    if (rest > 16) eval_batch<8, 6>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+    else if (rest > 8) eval_batch<4, 4>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+    else if (rest > 0) eval_batch<4, 2>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+}
+
+/* viso.cpp:711-722: the ratio test and the dense output record (best_idx, best_d1, best_d2, valid) */
+__device__ __forceinline__ void write_result(const MatchJob& job, const MatchParamsDev& P, int q, const BestState& st)
+{
+    int valid = 0;
+    const int b1 = st.bidx >= 0 ? (int)st.b1 : INT_MAX;
+    const int b2 = st.b2 == 0xffffffffu ? INT_MAX : (int)st.b2;
+    if (st.bidx >= 0) {
+        if (P.second_best) {
+            const double d2 = (b2 == INT_MAX) ? 1.7976931348623157e308 : (double)b2;
+            valid = ((double)b1 < d2 * P.ratio) ? 1 : 0; /* viso.cpp:715 */
+        } else
+            valid = 1;
+    }
+    job.out[q] = make_int4(st.bidx, b1, b2, valid);
+}
+
+/*
+ * match_desc for one query, viso.cpp:686-722, by one warp.
+ *
+ * Reference semantics restated set-wise: with D0 = L1(query, target 0) if that is <= radius
+ * (else +inf), the scanned candidates are the K smallest keys (L1, index) among
+ *     L = { j : L1_j <= radius and L1_j < D0 }
+ * (target 0 terminates the reference's scan, viso.cpp:693, and sorts first inside its distance group, so exactly
+ * the strictly closer points are scanned).  Over that set: best = min SAD, ties to the LARGEST key (the last one
+ * in scan order, viso.cpp:703), best_d2 = second smallest SAD with multiplicity.  Sampson-gated candidates
+ * (viso.cpp:695-701) still occupy a top-K slot but are not compared.  All of it is order independent.
+ *
+ * Phase 1: candidate generation through the visitor V (32 points per step, one per lane); when more than K points
+ * can be in range the exact top-K cut is found with a 128-bin histogram over the L1 distance plus an exact rank
+ * search inside the cut bin; the Sampson gate is applied and the survivors are appended to the per-warp list.
+ * Phase 2: eval_list() whenever the list may overflow on the next step, and once at the end.
+ * Returns the number of (query, candidate) pairs that reached the SAD.
+ */
+template <class V>
+__device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, const MatchParamsDev& P, WarpScratch& ws,
+                                                int lane, const uint4 qrec)
+{
+    const int q = (int)qrec.z;
+    const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
+    const unsigned qsum = qrec.w;
+    const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7);
+    const uint4 qa = __ldg(qp), qb = __ldg(qp + 8);
+    const float r = P.radius;
+    const int K = P.K;
+    const float bscale = (float)VISO_HIST_BINS / (r + 1.0f);
+    unsigned pairs = 0;
+
+    BestState st;
+    st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
+
+    /* index 0 terminator */
+    const float2 t0 = __ldg(job.t.xy);
+    const float d0 = l1_dist(qx, qy, t0.x, t0.y);
+    const float D0 = (d0 <= r) ? d0 : CUDART_INF_F;
+
+    /* top-K threshold: (Tbin, Td, Ti); candidates with bin < Tbin, or bin == Tbin and key <= (Td,Ti) */
+    int Tbin = INT_MAX;
+    float Td = CUDART_INF_F;
+    int Ti = INT_MAX;
+    if (vis.bound() > K) {
+        for (int b = lane; b < VISO_HIST_BINS; b += 32) ws.sel.hist[b] = 0;
+        __syncwarp();
+        int cnt = 0;
+        vis.all([&](bool in, float dist, uint4 rec) {
+            const bool inL = in && dist <= r && dist < D0;
+            if (inL) atomicAdd(&ws.sel.hist[dist_bin(dist, bscale)], 1u);
+            cnt += __popc(__ballot_sync(FULL, inL));
+        });
+        __syncwarp();
+        if (cnt > K) {
+            /* find the bin where the cumulative count reaches K */
+            unsigned c[4];
+            unsigned s = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { c[e] = ws.sel.hist[lane * 4 + e]; s += c[e]; }
+            const int incl = warp_incl_scan((int)s, lane);
+            const unsigned hit = __ballot_sync(FULL, incl >= K);
+            const int hl = __ffs(hit) - 1;
+            int tb = 0, before = 0;
+            if (lane == hl) {
+                int run = incl - (int)s;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (run + (int)c[e] >= K) { tb = lane * 4 + e; before = run; break; }
+                    run += (int)c[e];
+                }
+            }
+            tb = __shfl_sync(FULL, tb, hl);
+            before = __shfl_sync(FULL, before, hl);
+            const int nb = (int)ws.sel.hist[tb];
+            const int m = K - before; /* 1..nb keys of bin tb are kept */
+            Tbin = tb;
+            if (m < nb) {
+                if (nb <= VISO_TIE_CAP) {
+                    int fill = 0;
+                    vis.all([&](bool in, float dist, uint4 rec) {
+                        const bool hitb = in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb;
+                        const unsigned bm = __ballot_sync(FULL, hitb);
+                        if (hitb) {
+                            const int o = fill + __popc(bm & ((1u << lane) - 1));
+                            ws.sel.tieD[o] = dist;
+                            ws.sel.tieI[o] = (int)rec.z;
+                        }
+                        fill += __popc(bm);
+                    });
+                    __syncwarp();
+                    /* the key of rank m-1 inside the bin */
+                    float selD = 0.f; int selI = 0; bool have = false;
+                    for (int e = lane; e < nb; e += 32) {
+                        const float de = ws.sel.tieD[e]; const int ie = ws.sel.tieI[e];
+                        int rank = 0;
+                        for (int o = 0; o < nb; ++o) rank += key_greater(de, ie, ws.sel.tieD[o], ws.sel.tieI[o]) ? 1 : 0;
+                        if (rank == m - 1) { selD = de; selI = ie; have = true; }
+                    }
+                    const unsigned hm = __ballot_sync(FULL, have);
+                    const int sl = __ffs(hm) - 1;
+                    Td = __shfl_sync(FULL, selD, sl);
+                    Ti = __shfl_sync(FULL, selI, sl);
+                } else {
+                    /* pathological tie bin: m successive minimum searches (exact, slow) */
+                    float curD = -1.f; int curI = -1;
+                    for (int it = 0; it < m; ++it) {
+                        float bestD = CUDART_INF_F; int bestI = INT_MAX;
+                        vis.all([&](bool in, float dist, uint4 rec) {
+                            const int idx = (int)rec.z;
+                            if (in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb &&
+                                key_greater(dist, idx, curD, curI) && key_greater(bestD, bestI, dist, idx)) {
+                                bestD = dist; bestI = idx;
+                            }
+                        });
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float od = __shfl_xor_sync(FULL, bestD, o);
+                            const int oi = __shfl_xor_sync(FULL, bestI, o);
+                            if (key_greater(bestD, bestI, od, oi)) { bestD = od; bestI = oi; }
+                        }
+                        curD = bestD; curI = bestI;
+                    }
+                    Td = curD; Ti = curI;
+                }
+            }
+        }
+        __syncwarp(); /* the selection scratch is dead from here on: its storage becomes the list */
+    }
+
+    /* final pass: membership, Sampson gate, append to the list (membership of a point does not depend on the
+     * others once the threshold is known, so the list can be evaluated and reset at any time) */
+    int nlist = 0;
+    vis.all([&](bool in, float dist, uint4 rec) {
+        const int idx = (int)rec.z;
+        bool take = in && dist <= r && dist < D0;
+        if (take && Tbin != INT_MAX) {
+            const int bin = dist_bin(dist, bscale);
+            take = bin < Tbin || (bin == Tbin && !key_greater(dist, idx, Td, Ti));
+        }
+        if (take && P.epipolar) {
+            const double sd = sampson_dev(P.F, qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
+            if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
+        }
+        const unsigned tm = __ballot_sync(FULL, take);
+        if (tm == 0) return;
+        if (take) ws.list[nlist + __popc(tm & ((1u << lane) - 1))] = make_uint4(rec.z, __float_as_uint(dist), rec.w, 0u);
+        nlist += __popc(tm);
+        if (nlist > VISO_LIST_CAP - 32) {
+            __syncwarp();
+            eval_list(job.t.desc, ListAcc{ws}, nlist, lane, qa, qb, qsum, st);
+            pairs += nlist;
+            nlist = 0;
+            __syncwarp();
+        }
+    });
+    if (nlist > 0) {
+        __syncwarp();
+        eval_list(job.t.desc, ListAcc{ws}, nlist, lane, qa, qb, qsum, st);
+        pairs += nlist;
+        __syncwarp();
+    }
+
+    if (lane == 0) write_result(job, P, q, st);
+    return pairs;
+}
+
+/*
+ * sad_match_kernel: match_desc (viso.cpp:668-722) for a batch of jobs.  blockIdx.y = job, blockIdx.x = query tile
+ * (VISO_TILE_W x VISO_TILE_H cells of the QUERY set's grid, 96 x 64 px).
+ *
+ * 1. Staging.  The candidate records (x, y, index, row sum) of every target cell that can hold a neighbour of any of
+ *    the tile's queries -- the bounding box of the tile's query coordinates grown by radius + slack, clamped exactly
+ *    like the per-query geometry -- are copied to shared memory, one contiguous span per grid row (coalesced).
+ * 2. Candidate generation, LANE = QUERY.  Every warp walks a quarter of the staged points; the point is a shared
+ *    memory broadcast and each lane tests it against its own query (radius and index-0 terminator), appending hits
+ *    to that query's list (shared-memory counter).  ~9 instructions per 32 (query, point) tests and no ballots.
+ * 3. Evaluation, WARP = QUERY.  The list is gathered into candidate records (Sampson gate for the stereo mode,
+ *    lanes = candidates) and handed to eval_list().
+ * Queries whose neighbourhood holds more than max_neighbors points (the top-K cut is needed) or overflows the list,
+ * and tiles whose neighbourhood does not fit the staging buffer, are marked VISO_PENDING and counted; the generic
+ * kernel sad_match_generic_kernel, launched right after, completes exactly those (and exits at once when there are
+ * none).
+ */
+__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, VISO_MATCH_MINB)
+sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, int reg_cap, int ql_cap,
+                 unsigned long long* sad_pairs, int* n_pending)
+{
+    extern __shared__ uint4 reg[];                                /* staged neighbourhood, reg_cap records */
+    /* per-query candidate lists (region indices), 32 x (ql_cap + 2): the +2 makes the word stride odd so that
+     * lanes = queries write without bank conflicts */
+    unsigned short* const qlist = reinterpret_cast<unsigned short*>(reg + reg_cap);
+    const int ql_stride = ql_cap + 2;
+    __shared__ int qcnt[32];
+    __shared__ int row_off[VISO_MAX_REG_ROWS + 1];
+    __shared__ int tile_s[4];
+    __shared__ uint4 qrec_s[32];
+
+    const MatchJob job = jobs[blockIdx.y];
+    const MatchParamsDev& P = mp.p[job.mode];
+    const int nq = *job.q.n, nt = *job.t.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (g.gx + VISO_TILE_W - 1) / VISO_TILE_W;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    if (ty * VISO_TILE_H >= g.gy || nq <= 0) return;
+
+    /* the tile's queries: one span of the cell-sorted query array per cell row */
+    const int cx_lo = tx * VISO_TILE_W, cx_hi = min(cx_lo + VISO_TILE_W, g.gx);
+    int qtot = 0;
+    int qs[VISO_TILE_H], ql[VISO_TILE_H];
+#pragma unroll
+    for (int rr = 0; rr < VISO_TILE_H; ++rr) {
+        const int cy = ty * VISO_TILE_H + rr;
+        qs[rr] = 0; ql[rr] = 0;
+        if (cy < g.gy) {
+            qs[rr] = __ldg(job.q.cell_start + cy * g.gx + cx_lo);
+            ql[rr] = __ldg(job.q.cell_start + cy * g.gx + cx_hi) - qs[rr];
+        }
+        qtot += ql[rr];
+    }
+    if (qtot == 0) return;
+
+    auto query_rec = [&](int k) {
+        int pos = 0;
+#pragma unroll
+        for (int rr = 0; rr < VISO_TILE_H; ++rr) {
+            if (k >= 0 && k < ql[rr]) pos = qs[rr] + k;
+            k -= ql[rr];
+        }
+        return __ldg(job.q.srec + pos);
+    };
+
+    if (nt <= 0) { /* no targets: every query is unmatched */
+        for (int k = threadIdx.x; k < qtot; k += blockDim.x)
+            job.out[query_rec(k).z] = make_int4(-1, INT_MAX, INT_MAX, 0);
+        return;
+    }
+
+    /* Neighbourhood of the tile (warp 0): bounding box of the tile's query coordinates (queries outside the image
+     * extent are clamped into border cells, so the cell rectangle is not a bound), grown by radius + the largest
+     * per-query slack (make_geom) + a margin far above the float rounding of the sums; then the staged span of
+     * every grid row. */
+    const float r = P.radius;
+    if (warp == 0) {
+        float xmin = CUDART_INF_F, xmax = -CUDART_INF_F, ymin = CUDART_INF_F, ymax = -CUDART_INF_F, amax = 0.f;
+        for (int k = lane; k < qtot; k += 32) {
+            const uint4 qr = query_rec(k);
+            const float x = __uint_as_float(qr.x), y = __uint_as_float(qr.y);
+            xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+            amax = fmaxf(amax, fabsf(x) + fabsf(y));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = fminf(xmin, __shfl_xor_sync(FULL, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(FULL, xmax, o));
+            ymin = fminf(ymin, __shfl_xor_sync(FULL, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, o));
+            amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
+        }
+        const float grow = r + (1.0f + 4e-6f * (amax + r)) + 4e-6f * (amax + r) + 1e-3f;
+        const int cx0 = cell_coord(xmin - grow, g.gx), cx1 = cell_coord(xmax + grow, g.gx);
+        const int cy0 = cell_coord(ymin - grow, g.gy), cy1 = cell_coord(ymax + grow, g.gy);
+        const int nr = cy1 - cy0 + 1;
+        int total = -1; /* -1: no staging */
+        if (nr <= VISO_MAX_REG_ROWS && xmin == xmin && ymin == ymin && reg_cap > 0) {
+            int run = 0;
+            for (int b = 0; b < nr; b += 32) {
+                const int rr = b + lane;
+                int len = 0;
+                if (rr < nr) {
+                    const int cy = cy0 + rr;
+                    len = __ldg(job.t.cell_start + cy * g.gx + cx1 + 1) - __ldg(job.t.cell_start + cy * g.gx + cx0);
+                }
+                const int incl = warp_incl_scan(len, lane);
+                if (rr < nr) row_off[rr] = run + incl - len;
+                run += __shfl_sync(FULL, incl, 31);
+            }
+            if (lane == 0) row_off[nr] = run;
+            if (run <= reg_cap) total = run;
+        }
+        if (lane == 0) { tile_s[0] = cx0; tile_s[1] = cy0; tile_s[2] = nr; tile_s[3] = total; }
+    }
+    __syncthreads();
+    const int rcx0 = tile_s[0], rcy0 = tile_s[1], nrows = tile_s[2];
+    const bool tile_ok = tile_s[3] >= 0;
+
+    unsigned pairs = 0;
+    if (!tile_ok) { /* leave the whole tile to the generic kernel */
+        for (int k = threadIdx.x; k < qtot; k += blockDim.x) job.out[query_rec(k).z] = make_int4(0, 0, 0, VISO_PENDING);
+        if (threadIdx.x == 0) atomicAdd(n_pending, qtot);
+    } else {
+        const int R = tile_s[3];
+        for (int rr = warp; rr < nrows; rr += VISO_MATCH_WARPS) {
+            const int o = row_off[rr], len = row_off[rr + 1] - o;
+            const uint4* src = job.t.srec + __ldg(job.t.cell_start + (rcy0 + rr) * g.gx + rcx0);
+            for (int i = lane; i < len; i += 32) reg[o + i] = __ldg(src + i);
+        }
+        const float2 t0 = __ldg(job.t.xy);
+        for (int g0 = 0; g0 < qtot; g0 += 32) { /* groups of 32 queries: lane = query */
+            __syncthreads(); /* staging done (first round) / the previous group's lists are consumed */
+            if (threadIdx.x < 32) qcnt[threadIdx.x] = 0;
+            __syncthreads();
+            {
+                const int k = g0 + lane;
+                const bool act = k < qtot;
+                const uint4 qr = query_rec(act ? k : g0);
+                if (warp == 0) qrec_s[lane] = qr;
+                const float qx = __uint_as_float(qr.x), qy = __uint_as_float(qr.y);
+                const float d0 = l1_dist(qx, qy, t0.x, t0.y);
+                /* limit = min(radius, strictly below D0): candidates need dist <= r and dist < D0 (index-0 rule) */
+                const float D0 = (d0 <= r) ? d0 : CUDART_INF_F;
+                const float2* pts = reinterpret_cast<const float2*>(reg);
+#pragma unroll 4
+                for (int i = warp; i < R; i += VISO_MATCH_WARPS) {
+                    const float2 p = pts[2 * i]; /* (x, y) of the uint4 record: broadcast */
+                    const float dist = l1_dist(qx, qy, p.x, p.y);
+                    if (act && dist <= r && dist < D0) {
+                        const int j = atomicAdd(&qcnt[lane], 1);
+                        if (j < ql_cap) qlist[lane * ql_stride + j] = (unsigned short)i;
+                    }
+                }
+            }
+            __syncthreads();
+            const int gq = min(32, qtot - g0);
+            for (int kk = warp; kk < gq; kk += VISO_MATCH_WARPS) {
+                const uint4 qrec = qrec_s[kk];
+                const int n = qcnt[kk];
+                if (n > ql_cap || n > P.K) { /* top-K cut or list overflow: left to the generic kernel */
+                    if (lane == 0) {
+                        job.out[qrec.z] = make_int4(0, 0, 0, VISO_PENDING);
+                        atomicAdd(n_pending, 1);
+                    }
+                    continue;
+                }
+                const int q = (int)qrec.z;
+                const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
+                const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7);
+                const uint4 qa = __ldg(qp), qb = __ldg(qp + 8);
+                BestState st;
+                st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
+                unsigned short* ql = qlist + kk * ql_stride;
+                int nlist = n;
+                if (P.epipolar) { /* Sampson gate (viso.cpp:695-701), lanes = candidates, compacting the list in place */
+                    nlist = 0;
+                    for (int base = 0; base < n; base += 32) {
+                        const int e = base + lane;
+                        bool take = e < n;
+                        const unsigned short ri = ql[take ? e : 0];
+                        if (take) {
+                            const uint4 rec = reg[ri];
+                            const double sd = sampson_dev(P.F, qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
+                            if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
+                        }
+                        const unsigned tm = __ballot_sync(FULL, take);
+                        __syncwarp(); /* every lane has read its entry before the slots are reused */
+                        if (take) ql[nlist + __popc(tm & ((1u << lane) - 1))] = ri;
+                        nlist += __popc(tm);
+                    }
+                    __syncwarp();
+                }
+                if (nlist > 0) eval_list(job.t.desc, TileAcc{ql, reg, qx, qy}, nlist, lane, qa, qb, qrec.w, st);
+                pairs += nlist;
+                if (lane == 0) write_result(job, P, q, st);
+            }
+        }
+    }
+    if (sad_pairs && lane == 0 && pairs) {
+        atomicAdd(sad_pairs, (unsigned long long)pairs);
+        atomicAdd(sad_pairs + 1, (unsigned long long)pairs);
+    }
+}
+
+/*
+ * Generic match kernel: CTA = VISO_STRIP_QPC consecutive cell-sorted queries, one warp per query, every query walks
+ * its own grid-row spans in global memory and applies the exact top-K cut (match_query<GlobalVisitor>).  Handles any
+ * radius, max_neighbors and density.  With only_pending it completes the queries the tile kernel marked
+ * VISO_PENDING; VISO_MATCH_MODE=generic runs everything through it (A/B measurements and tests).
+ */
+__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32)
+sad_match_generic_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, unsigned long long* sad_pairs,
+                         const int* __restrict__ n_pending, int only_pending)
+{
+    __shared__ WarpScratch wscr[VISO_MATCH_WARPS];
+    if (only_pending && *n_pending == 0) return;
+    const MatchJob job = jobs[blockIdx.y];
+    const MatchParamsDev& P = mp.p[job.mode];
+    const int nq = *job.q.n, nt = *job.t.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpScratch& ws = wscr[warp];
+    unsigned pairs = 0;
+    for (int chunk = blockIdx.x; chunk * VISO_STRIP_QPC < nq; chunk += gridDim.x)
+    for (int qi = chunk * VISO_STRIP_QPC + warp; qi < min(nq, (chunk + 1) * VISO_STRIP_QPC); qi += VISO_MATCH_WARPS) {
+        const uint4 qrec = __ldg(job.q.srec + qi);
+        if (only_pending && job.out[qrec.z].w != VISO_PENDING) continue;
+        if (nt <= 0) {
+            if (lane == 0) job.out[qrec.z] = make_int4(-1, INT_MAX, INT_MAX, 0);
+            continue;
+        }
+        GlobalVisitor vis{job.t, g, make_geom(g, __uint_as_float(qrec.x), __uint_as_float(qrec.y), P.radius), ws, lane, 0, true};
+        pairs += match_query(vis, job, P, ws, lane, qrec);
+    }
+    if (sad_pairs && lane == 0 && pairs) {
+        atomicAdd(sad_pairs, (unsigned long long)pairs);
+        atomicAdd(sad_pairs + 1, (unsigned long long)pairs);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ launchers */
+
+cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dlen, int* err_flag, cudaStream_t s)
+{
+    if (n_jobs <= 0 || max_n <= 0) return cudaSuccess;
+    dim3 grid((max_n + 7) / 8, n_jobs);
+    pack_desc_kernel<<<grid, 256, 0, s>>>(jobs, dlen, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_extract(const ExtractJob* jobs, int n_jobs, int max_n, int width, int height, int pitch, int radius,
+                                cudaStream_t s)
+{
+    if (n_jobs <= 0 || max_n <= 0) return cudaSuccess;
+    dim3 grid((max_n + 8 * VISO_EXTRACT_KPW - 1) / (8 * VISO_EXTRACT_KPW), n_jobs);
+    if (radius != 5) return cudaErrorInvalidValue; /* the pipeline's descriptor radius (viso.cpp:1174) */
+    extract_desc_kernel<5><<<grid, 256, 0, s>>>(jobs, width, height, pitch);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStream_t s)
+{
+    if (n_jobs <= 0) return cudaSuccess;
+    const size_t smem = (size_t)(2 * g.gx * g.gy + 1) * sizeof(int);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    grid_build_kernel<<<n_jobs, 512, smem, s>>>(jobs, g);
+    return cudaGetLastError();
+}
+
+cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
+                              GridCfg g, unsigned long long* sad_pairs, int* n_pending, cudaStream_t s, int* launches)
+{
+    if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+    static int mode = -1;
+    if (mode < 0) {
+        const char* m = getenv("VISO_MATCH_MODE");
+        mode = (m && m[0] == 'g') ? 1 : 0;
+    }
+    /* the generic kernel loops over query chunks: about 16 CTAs per SM in total, never more than one per chunk */
+    const int gchunks = (max_nq + VISO_STRIP_QPC - 1) / VISO_STRIP_QPC;
+    const dim3 ggrid(std::min(gchunks, std::max(1, (148 * 16 + n_jobs - 1) / n_jobs)), n_jobs);
+    if (mode == 1) {
+        sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, n_pending, 0);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
+    /* staging capacity for a tile's neighbourhood: twice the expected point count of the grown tile box at the
+     * densest target set, within [256, 6144] records of 16 bytes */
+    const float r = fmaxf(mp.p[0].radius, mp.p[1].radius);
+    const double ext_x = (double)g.gx * VISO_GRID_CS, ext_y = (double)g.gy * VISO_GRID_CS;
+    const double bx = fmin(ext_x, VISO_TILE_W * VISO_GRID_CS + 2.0 * (r + 2) + 2 * VISO_GRID_CS);
+    const double by = fmin(ext_y, VISO_TILE_H * VISO_GRID_CS + 2.0 * (r + 2) + 2 * VISO_GRID_CS);
+    double expect = (double)max_nt * (bx * by) / (ext_x * ext_y);
+    if (!(expect >= 0)) expect = 0;
+    int cap = (int)fmin(6144.0, fmax(256.0, 2.0 * expect + 64.0));
+    cap = (cap + 63) & ~63;
+    /* per-query list capacity: twice the expected number of points in the L1 diamond (2 r^2), 64..256 */
+    const double in_diamond = (double)max_nt * fmin(1.0, 2.0 * (double)r * r / (ext_x * ext_y));
+    int ql_cap = (int)fmin(256.0, fmax(64.0, 2.0 * in_diamond + 16.0));
+    ql_cap = (ql_cap + 31) & ~31;
+    const size_t smem = (size_t)cap * sizeof(uint4) + (size_t)32 * (ql_cap + 2) * sizeof(unsigned short);
+    static int attr_set = 0;
+    if (smem > 24 * 1024 && !attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             6144 * 16 + 32 * 258 * 2);
+        if (e != cudaSuccess) return e;
+        attr_set = 1;
+    }
+    cudaError_t e = cudaMemsetAsync(n_pending, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    const int tiles = ((g.gx + VISO_TILE_W - 1) / VISO_TILE_W) * ((g.gy + VISO_TILE_H - 1) / VISO_TILE_H);
+    sad_match_kernel<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, ql_cap, sad_pairs, n_pending);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, n_pending, 1);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}

@@ -1,5 +1,5 @@
 /*
- * viso_dev.h -- device-side data layout shared by kernels.cu and capi.cu (not part of the public ABI).
+ * viso_dev.h -- device-side data layout shared by the kernel translation units (match.cu, sort_circle.cu, estimation.cu, geometry.cu) and capi.cu (not part of the public ABI).
  *
  * HBM layout (see DESIGN.md "Data layout"):
  *   keypoints        float2[n]                      original order (index = the reference's keypoint index)
@@ -151,7 +151,7 @@ struct CircleJob {             /* per frame pair */
     int pad;
 };
 
-/* launch wrappers (kernels.cu).  All enqueue on `s` and return cudaGetLastError(). */
+/* launch wrappers (defined next to their kernels).  All enqueue on `s` and return cudaGetLastError(). */
 cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dlen, int* err_flag, cudaStream_t s);
 cudaError_t viso_launch_extract(const ExtractJob* jobs, int n_jobs, int max_n, int width, int height, int pitch, int radius,
                                 cudaStream_t s);
