@@ -1,0 +1,52 @@
+/*
+ * capi_internal.h -- definitions shared by the C-ABI translation units (capi.cu: context, standalone entry points,
+ * host bookkeeping; capi_seq.cu: the batched sequence pipeline).  Not part of the public ABI.
+ */
+#ifndef VISO_CAPI_INTERNAL_H_
+#define VISO_CAPI_INTERNAL_H_
+
+#include "../../include/viso_b200.h"
+#include "viso_dev.h"
+
+#include <string>
+
+/* ------------------------------------------------------------------------------------------------ context */
+
+struct viso_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    GridCfg grid{78, 24}; /* 1248 x 384 px in 16-px cells */
+    char* d_scr = nullptr;
+    size_t d_cap = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaStream_t copy_stream = nullptr;   /* host -> device uploads of sequence objects (overlap with compute) */
+
+    int fail(int code, const std::string& msg)
+    {
+        err = msg;
+        return code;
+    }
+    int fail_cuda(cudaError_t e, const char* what)
+    {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return VISO_ERR_CUDA;
+    }
+    int ncell() const { return grid.gx * grid.gy; }
+};
+
+#define CK(call)                                                        \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return ctx->fail_cuda(e__, #call);      \
+    } while (0)
+
+
+namespace viso_capi {
+ParamDev make_param_dev(const viso_param* p);
+MatchParamsDev make_match_dev(const viso_match_params* p);
+int status_from_flags(viso_ctx* ctx, int flags);
+} // namespace viso_capi
+
+#endif
