@@ -58,11 +58,14 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
  * with sobel_x = cv::Sobel(image, CV_32F, 1, 0, 3, 1, 0, BORDER_REFLECT_101) (:1010), i.e. the integer
  *     (I(y-1,x+1) + 2 I(y,x+1) + I(y+1,x+1)) - (I(y-1,x-1) + 2 I(y,x-1) + I(y+1,x-1)),  index -1 -> 1, n -> n-2.
  * Values are integers in [-1020, 1020]; the row is written biased (+1024) in the u16 layout with its sum.
- * One warp per keypoint.  The (2R+3)^2 source window is first staged in shared memory with the reflection already
- * applied (6 byte loads per lane, ~3 image rows per load instruction instead of 11), then lane l computes elements
- * 4l..4l+3 from the staged window.
+ * Half a warp per keypoint, lane = column of the (2R+3)-pixel-wide source window: the lane loads its column (one
+ * byte per window row; a row of the window is one contiguous run for the half warp), forms the vertical [1 2 1] sums
+ * in registers, and the horizontal difference s(x+1) - s(x-1) comes from the lane two to the right by shuffle.
+ * The 121 values go through a 256-byte shared-memory row to reach the packed layout (16 bytes per lane) and the row
+ * sum.  The image is touched once per frame, so the loads mostly miss to DRAM: a warp issues the loads of
+ * VISO_EXTRACT_ROUNDS x 2 keypoints before using any.
  */
-#define VISO_EXTRACT_WIN 16 /* staged window pitch; supports radius <= 6 (2R+3 <= 15) */
+#define VISO_EXTRACT_ROUNDS 2
 
 __device__ __forceinline__ int reflect101(int i, int n)
 {
@@ -71,78 +74,72 @@ __device__ __forceinline__ int reflect101(int i, int n)
     return min(max(i, 0), n - 1); /* far outside: any in-range pixel, the sample is masked to 0 anyway */
 }
 
-#define VISO_EXTRACT_KPW 4 /* keypoints per warp iteration: their image loads are all in flight together */
-
 template <int radius>
 __global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __restrict__ jobs, int width, int height, int pitch)
 {
-    __shared__ unsigned char win_s[8][VISO_EXTRACT_KPW][VISO_EXTRACT_WIN * VISO_EXTRACT_WIN];
+    constexpr int side = 2 * radius + 1, dlen = side * side, wside = side + 2;
+    static_assert(wside <= 16 && dlen <= VISO_DESC_U16, "half a warp per keypoint: radius <= 6");
+    __shared__ __align__(16) unsigned short out_s[8][VISO_EXTRACT_ROUNDS][2][VISO_DESC_U16];
     const ExtractJob job = jobs[blockIdx.y];
     if (!*job.from_image) return;
     const int n = *job.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int side = 2 * radius + 1, dlen = side * side, wside = side + 2, wn = wside * wside;
-    constexpr int NL = (wn + 31) / 32;
-    for (int row0 = (blockIdx.x * 8 + warp) * VISO_EXTRACT_KPW; row0 < n; row0 += gridDim.x * 8 * VISO_EXTRACT_KPW) {
-        int px[VISO_EXTRACT_KPW], py[VISO_EXTRACT_KPW];
-        unsigned char pix[VISO_EXTRACT_KPW][NL];
-        /* the image is touched once per frame, so these loads mostly miss to DRAM: issue all of them first */
+    const int half = lane >> 4, col = lane & 15;
+    constexpr int KPW = 2 * VISO_EXTRACT_ROUNDS;
+    /* the pad elements of the staging rows stay zero */
+    for (int i = lane; i < VISO_EXTRACT_ROUNDS * 2 * VISO_DESC_U16; i += 32) (&out_s[warp][0][0][0])[i] = 0;
+    __syncwarp();
+    for (int row0 = (blockIdx.x * 8 + warp) * KPW; row0 < n; row0 += gridDim.x * 8 * KPW) {
+        int px[VISO_EXTRACT_ROUNDS], py[VISO_EXTRACT_ROUNDS];
+        bool interior[VISO_EXTRACT_ROUNDS];
+        unsigned char p[VISO_EXTRACT_ROUNDS][wside];
 #pragma unroll
-        for (int q = 0; q < VISO_EXTRACT_KPW; ++q) {
-            const float2 kp = job.kp[min(row0 + q, n - 1)];
+        for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
+            const float2 kp = job.kp[min(row0 + 2 * q + half, n - 1)];
             px[q] = __float2int_rn(kp.x); py[q] = __float2int_rn(kp.y);
+            /* the whole window inside the image: no reflection, no masked sample (uniform over the half warp) */
+            interior[q] = px[q] > radius && px[q] + radius + 1 < width && py[q] > radius && py[q] + radius + 1 < height;
+            const int cx = min(col, wside - 1); /* lanes beyond the window repeat its last column */
+            if (interior[q]) {
+                const unsigned char* base = job.img + (size_t)(py[q] - radius - 1) * pitch + (px[q] - radius - 1 + cx);
 #pragma unroll
-            for (int j = 0; j < NL; ++j) {
-                const int idx = min(lane + 32 * j, wn - 1);
-                const int wy = idx / wside, wx = idx - wy * wside;
-                const int iy = reflect101(py[q] - radius - 1 + wy, height), ix = reflect101(px[q] - radius - 1 + wx, width);
-                pix[q][j] = __ldg(job.img + (size_t)iy * pitch + ix);
+                for (int r = 0; r < wside; ++r) p[q][r] = __ldg(base + r * pitch);
+            } else {
+                const int ix = reflect101(px[q] - radius - 1 + cx, width);
+#pragma unroll
+                for (int r = 0; r < wside; ++r)
+                    p[q][r] = __ldg(job.img + (size_t)reflect101(py[q] - radius - 1 + r, height) * pitch + ix);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
+            unsigned short* orow = out_s[warp][q][half];
+#pragma unroll
+            for (int r = 0; r < side; ++r) {
+                const int sv = (int)p[q][r] + 2 * (int)p[q][r + 1] + (int)p[q][r + 2]; /* column cx, image rows y-1..y+1 */
+                int sob = __shfl_down_sync(FULL, sv, 2, 16) - sv;                       /* s(x+1) - s(x-1), x = px-R+col */
+                if (!interior[q]) {
+                    const int y = py[q] + r - radius, x = px[q] + col - radius;
+                    if (!(y > 0 && y < height && x > 0 && x < width)) sob = 0;           /* viso.cpp:1018 */
+                }
+                if (col < side) orow[r * side + col] = (unsigned short)(sob + 1024);
             }
         }
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < VISO_EXTRACT_KPW; ++q)
+        for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
+            const int row = row0 + 2 * q + half;
+            const uint4 w = reinterpret_cast<const uint4*>(out_s[warp][q][half])[col];
+            unsigned sum = (w.x & 0xffffu) + (w.x >> 16) + (w.y & 0xffffu) + (w.y >> 16) + (w.z & 0xffffu) + (w.z >> 16) +
+                           (w.w & 0xffffu) + (w.w >> 16);
 #pragma unroll
-            for (int j = 0; j < NL; ++j) {
-                const int idx = lane + 32 * j;
-                if (idx < wn) {
-                    const int wy = idx / wside, wx = idx - wy * wside;
-                    win_s[warp][q][wy * VISO_EXTRACT_WIN + wx] = pix[q][j];
-                }
+            for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o, 16);
+            if (row < n) {
+                reinterpret_cast<uint4*>(job.out + (size_t)row * VISO_DESC_U16)[col] = w;
+                if (col == 0) job.rsum[row] = sum;
             }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < VISO_EXTRACT_KPW; ++q) {
-            const int row = row0 + q;
-            if (row >= n) break; /* warp uniform */
-            const unsigned char* win = win_s[warp][q];
-            unsigned u[4];
-            unsigned sum = 0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = lane * 4 + e;
-                unsigned v = 0;
-                if (k < dlen) {
-                    const int r = k / side, c = k - r * side;
-                    const int y = py[q] + r - radius, x = px[q] + c - radius;
-                    int sob = 0;
-                    if (y > 0 && y < height && x > 0 && x < width) {
-                        const unsigned char* w0 = win + r * VISO_EXTRACT_WIN + c; /* window row r = image row y-1 */
-                        sob = ((int)w0[2] + 2 * (int)w0[VISO_EXTRACT_WIN + 2] + (int)w0[2 * VISO_EXTRACT_WIN + 2]) -
-                              ((int)w0[0] + 2 * (int)w0[VISO_EXTRACT_WIN] + (int)w0[2 * VISO_EXTRACT_WIN]);
-                    }
-                    v = (unsigned)(sob + 1024);
-                }
-                u[e] = v;
-                sum += v;
-            }
-            uint2 w;
-            w.x = u[0] | (u[1] << 16);
-            w.y = u[2] | (u[3] << 16);
-            reinterpret_cast<uint2*>(job.out + (size_t)row * VISO_DESC_U16)[lane] = w;
-            const unsigned tot = warp_sum_u(sum);
-            if (lane == 0) job.rsum[row] = tot;
         }
+        __syncwarp();
     }
 }
 
@@ -921,7 +918,7 @@ cudaError_t viso_launch_extract(const ExtractJob* jobs, int n_jobs, int max_n, i
                                 cudaStream_t s)
 {
     if (n_jobs <= 0 || max_n <= 0) return cudaSuccess;
-    dim3 grid((max_n + 8 * VISO_EXTRACT_KPW - 1) / (8 * VISO_EXTRACT_KPW), n_jobs);
+    dim3 grid((max_n + 16 * VISO_EXTRACT_ROUNDS - 1) / (16 * VISO_EXTRACT_ROUNDS), n_jobs);
     if (radius != 5) return cudaErrorInvalidValue; /* the pipeline's descriptor radius (viso.cpp:1174) */
     extract_desc_kernel<5><<<grid, 256, 0, s>>>(jobs, width, height, pitch);
     return cudaGetLastError();
