@@ -328,6 +328,8 @@ __global__ void __launch_bounds__(256) ransac_score_kernel(const RansacProb* __r
     if (lane == 0) pb.hyp_count[hId] = cnt;
 }
 
+#define VISO_GN_STAGE 512 /* Jacobian rows staged in shared memory per round of the sequential sums (28 KB) */
+
 /*
  * Block-cooperative minimize_reproj (viso.cpp:1583-1623) over an arbitrary active set.  Per iteration:
  * all threads write Jacobian rows + residuals to `scratch` ([4*na][7]); lanes 0..26 of warp 0 then form the 21
@@ -336,7 +338,8 @@ __global__ void __launch_bounds__(256) ransac_score_kernel(const RansacProb* __r
  */
 __device__ int gn_block(const double* __restrict__ X, const double* __restrict__ obs, int stride, int n,
                         const int* __restrict__ active, int na, double* tr_s, const ParamDev& P,
-                        double* __restrict__ scratch, double* sums_s /* smem[27] */, int* flag_s /* smem */)
+                        double* __restrict__ scratch, double* sums_s /* smem[27] */, int* flag_s /* smem */,
+                        double* stage_s /* smem[VISO_GN_STAGE * 7] */)
 {
     for (int it = 0; it < 100; ++it) {
         double tr[6];
@@ -357,13 +360,24 @@ __device__ int gn_block(const double* __restrict__ X, const double* __restrict__
                 for (int c = 0; c < 7; ++c) scratch[(size_t)(4 * i + r) * 7 + c] = rows[r][c];
         }
         __syncthreads();
-        if (threadIdx.x < 27) {
-            const int a = c_pair_a[threadIdx.x], b = c_pair_b[threadIdx.x];
+        {
+            /* the rows come back through shared memory, VISO_GN_STAGE rows at a time (coalesced, all threads), so the
+             * 27 sequential accumulation chains read with shared-memory latency instead of L2 latency; the order of
+             * the additions is unchanged: chunks in order, rows ascending inside a chunk */
+            const int a = threadIdx.x < 27 ? c_pair_a[threadIdx.x] : 0, b = threadIdx.x < 27 ? c_pair_b[threadIdx.x] : 0;
             double s = 0;
             const int rowsN = 4 * na;
-#pragma unroll 4
-            for (int k = 0; k < rowsN; ++k) s += scratch[(size_t)k * 7 + a] * scratch[(size_t)k * 7 + b];
-            sums_s[threadIdx.x] = s;
+            for (int k0 = 0; k0 < rowsN; k0 += VISO_GN_STAGE) {
+                const int cnt = min(VISO_GN_STAGE, rowsN - k0);
+                for (int e = threadIdx.x; e < cnt * 7; e += blockDim.x) stage_s[e] = scratch[(size_t)k0 * 7 + e];
+                __syncthreads();
+                if (threadIdx.x < 27) {
+#pragma unroll 8
+                    for (int k = 0; k < cnt; ++k) s += stage_s[k * 7 + a] * stage_s[k * 7 + b];
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x < 27) sums_s[threadIdx.x] = s;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -426,6 +440,7 @@ __global__ void __launch_bounds__(256) ransac_final_kernel(const RansacProb* __r
     __shared__ int best_cnt_s[256], best_idx_s[256];
     __shared__ double tr_s[6];
     __shared__ double sums_s[27];
+    __shared__ double stage_s[VISO_GN_STAGE * 7];
     __shared__ int flag_s;
     const RansacProb& pb = probs[blockIdx.x];
     const int n = *pb.n;
@@ -466,7 +481,7 @@ __global__ void __launch_bounds__(256) ransac_final_kernel(const RansacProb* __r
     int ok = 0, n_inl = n_act;
     const int* list = pb.active;
     if (n_act >= 6) {
-        ok = gn_block(pb.X, pb.obs, pb.stride, n, pb.active, n_act, tr_s, P, pb.scratch, sums_s, &flag_s);
+        ok = gn_block(pb.X, pb.obs, pb.stride, n, pb.active, n_act, tr_s, P, pb.scratch, sums_s, &flag_s, stage_s);
         if (ok) {
             n_inl = inliers_block(pb.X, pb.obs, pb.stride, n, tr_s, P, pb.inliers, warp_tot);
             list = pb.inliers;
@@ -487,10 +502,11 @@ __global__ void __launch_bounds__(256) gn_kernel(const double* X, const double* 
 {
     __shared__ double tr_s[6];
     __shared__ double sums_s[27];
+    __shared__ double stage_s[VISO_GN_STAGE * 7];
     __shared__ int flag_s;
     if (threadIdx.x < 6) tr_s[threadIdx.x] = tr[threadIdx.x];
     __syncthreads();
-    const int r = gn_block(X, obs, stride, stride, active, na, tr_s, P, scratch, sums_s, &flag_s);
+    const int r = gn_block(X, obs, stride, stride, active, na, tr_s, P, scratch, sums_s, &flag_s, stage_s);
     __syncthreads();
     if (threadIdx.x < 6) tr[threadIdx.x] = tr_s[threadIdx.x];
     if (threadIdx.x == 0) *ok = r;
