@@ -100,7 +100,7 @@ void viso_param_default(viso_param* p);                                 /* param
  * kp: n x 2 float (x,y); d: n x desc_len float.  Dense per-query outputs (n1 each, host):
  *   best_idx (-1: none), best_d1, best_d2 (INT32_MAX: none), valid (1 iff the reference pushes a Match).
  * The caller compacts valid rows in query order into Match(i,best_idx,best_d1) and applies std::sort by dist
- * (viso.cpp:724); libviso_b200/host/viso.cpp does exactly that. */
+ * (viso.cpp:724), or calls viso_match_desc_sorted / viso_sort_matches, which do both on the device. */
 int viso_match_desc(viso_ctx* ctx, const float* kp1, int n1, const float* kp2, int n2,
                     const float* d1, const float* d2, int desc_len, const viso_match_params* params,
                     int32_t* best_idx, int32_t* best_d1, int32_t* best_d2, int32_t* valid);

@@ -7,7 +7,8 @@
  * matches decides the column order of the RANSAC inputs, which the reference's weight indexing quirk
  * (viso.cpp:1449) and the sample table make observable.  Bit-exact parity therefore needs the exact permutation
  * libstdc++ produces.  This file restates the algorithm (no recursion, explicit stack) so the SAME code runs in a
- * CUDA thread on the device and under g++ in tests/test_introsort.py, where it is compared with std::sort itself.
+ * CUDA thread on the device and under g++ in tests/test_oracle_golden.py (tests/introsort_check.cpp), where it is compared with std::sort itself; the
+ * device additionally runs a warp-parallel equivalent (sort_circle.cu) checked against this one.
  */
 #ifndef VISO_INTROSORT_H_
 #define VISO_INTROSORT_H_

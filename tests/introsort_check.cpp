@@ -1,4 +1,4 @@
-// Host harness for tests/test_introsort.py: runs the restated introsort (libviso_b200/csrc/introsort.h, the code
+// Host harness for tests/test_oracle_golden.py::test_sort_matches_is_libstdcxx_std_sort: runs the restated introsort (libviso_b200/csrc/introsort.h, the code
 // the device executes) and libstdc++'s std::sort (what the reference calls at viso.cpp:724) on the same input.
 #include <algorithm>
 #include <cstring>
