@@ -152,7 +152,7 @@ def make_seeds(n_frames, H, seed):
     return np.random.default_rng(424242 + seed).integers(0, 2 ** 32, size=(n_frames, H, 3), dtype=np.uint32)
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, guard):
     """--impl reference: the reference's CPU path (oracle port) on the host cores"""
     if rank != 0:
         return
@@ -191,7 +191,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    guard.emit(json.dumps(line))
 
 
 _REF_STATE = None
@@ -216,13 +216,30 @@ def workload_config(args):
             "parallelism": f"{args.gpus} independent sequence(s), one per GPU, NCCL gather of 64-byte records"}
 
 
+class StdoutGuard:
+    """stdout must carry exactly one JSON line: point fd 1 at stderr while libraries (NCCL's version banner, ...) may
+    print, and give it back for the result"""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    guard = StdoutGuard()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, guard)
         return
 
     import torch
@@ -401,7 +418,7 @@ def main():
             line["cpu_baseline"] = {"value": npairs / secs, "unit": "frame-pairs/s", "cores": 1, "kind": "port",
                                     "sample": f"first {npairs} frame pairs of the same sequence, CPU oracle "
                                               f"(g++ -O2), {secs:.1f} s", "records_match_gpu": bool(same)}
-        print(json.dumps(line), flush=True)
+        guard.emit(json.dumps(line))
     seq.close()
     ctx.close()
     if world > 1:
