@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libviso_oracle.so")
+_SO = os.environ.get("VISO_ORACLE_SO") or os.path.join(_HERE, "libviso_oracle.so")  # override: tools/cpu_baseline.py (-O0 build)
 
 
 def build(force=False):
@@ -19,7 +19,7 @@ def build(force=False):
     if (not force and os.path.exists(_SO)
             and os.path.getmtime(_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
         return _SO
-    subprocess.check_call(["make", "-C", _HERE, "-B", "libviso_oracle.so"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _HERE, "-B", os.path.basename(_SO)], stdout=subprocess.DEVNULL)
     return _SO
 
 
