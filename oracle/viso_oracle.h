@@ -12,7 +12,9 @@
  * third-party arithmetic on the path (OpenCV cvflann radiusSearch ordering, cv::mulTransposed,
  * cv::solve(DECOMP_LU), cv::invert, cv::determinant, cv::Sobel) IS pinned: the restatements
  * below are checked bit-for-bit against cv2 4.13 and the resulting vectors are committed under
- * tests/golden/ (generator: tools/make_golden.py).
+ * tests/golden/ (generator: tools/make_golden.py).  The glue between them is checked against tests/golden/path_cv2.npz,
+ * a literal Python transcription of viso.cpp's control flow that executes the real OpenCV routine at every third-party
+ * call site (tools/make_golden_path.py).  No reference BINARY output exists to pin against.
  *
  * All matrices are row-major, like cv::Mat.
  */

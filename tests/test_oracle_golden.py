@@ -258,3 +258,73 @@ def test_sequence_recovers_ground_truth_motion(oracle, small_sequence):
         lr = out["lr_matches"][t]
         assert (np.diff(lr[:, 2]) >= 0).all() and len(np.unique(lr[:, 0])) == len(lr)
     assert len(out["poses"]) == len(frames)
+
+
+# ------------------------------------------------------------------------------------------------ cv2 transcription
+
+def _dense_matches(o, g):
+    want = np.stack([o["idx"], o["d1"], o["d2"], o["valid"]], 1).astype(np.int64)
+    assert np.array_equal(want, g)
+
+
+def test_path_against_cv2_transcription(oracle):
+    """tests/golden/path_cv2.npz (tools/make_golden_path.py): the reference's control flow transcribed literally with the
+    REAL OpenCV calls at every third-party call site (cvflann radiusSearch, cv::norm, mulTransposed, gemm, solve,
+    invert).  Integer results must be identical, tr / poses agree to 1e-9 (gemm's accumulation order)."""
+    g = load("path_cv2.npz")
+    F, P1, P2 = g["F"], g["P1"], g["P2"]
+    assert np.array_equal(oracle.F_from_P(P1, P2), F)
+    stereo, temporal = oracle.match_params_stereo(F), oracle.match_params_temporal()
+    p = oracle.param_default(base=abs(P2[0, 3] / P2[0, 0]), f=P1[0, 0], cu=P1[0, 2], cv=P1[1, 2], ransac_iter=12)
+    fr = [{k: g[f"f{t}_{k}"] for k in ("kpL", "kpR", "dL", "dR")} for t in range(3)]
+    lr, xs, Xs = [], [], []
+    for t, f in enumerate(fr):
+        o = oracle.match_desc(f["kpL"], f["kpR"], f["dL"], f["dR"], stereo)
+        _dense_matches(o, g[f"lr{t}_dense"])
+        assert np.array_equal(o["matches"], oracle.sort_matches(g[f"lr{t}_push"]))   # push order -> std::sort order
+        lr.append(o["matches"])
+        x = oracle.collect_matches(f["kpL"], f["kpR"], o["matches"])
+        X = oracle.triangulate_rectified_f64(x, p.f, p.base, p.cu, p.cv)
+        assert np.array_equal(x, g[f"x{t}"]) and np.array_equal(X, g[f"X{t}"])
+        xs.append(x); Xs.append(X)
+    pose = np.eye(4)
+    n_pose = 1
+    for t in (1, 2):
+        f, fp = fr[t], fr[t - 1]
+        o11 = oracle.match_desc(f["kpL"], fp["kpL"], f["dL"], fp["dL"], temporal)
+        o22 = oracle.match_desc(f["kpR"], fp["kpR"], f["dR"], fp["dR"], temporal)
+        _dense_matches(o11, g[f"m11_{t}_dense"])
+        _dense_matches(o22, g[f"m22_{t}_dense"])
+        circ, pcl = oracle.match_circle(lr[t], lr[t - 1], o11["matches"], o22["matches"])
+        assert np.array_equal(circ, g[f"circ{t}"]) and np.array_equal(pcl[:, :2], g[f"pcl{t}"])
+        assert len(circ) >= 20
+        x_c = np.ascontiguousarray(xs[t][:, pcl[:, 0]]); Xp_c = np.ascontiguousarray(Xs[t - 1][:, pcl[:, 1]])
+        table = oracle.samples_from_seeds(g["seeds"][t], len(circ))
+        assert np.array_equal(table, g[f"table{t}"])
+        r = oracle.ransac_minimize_reproj(Xp_c, x_c, p, table)
+        assert r["ok"] == bool(g[f"ok{t}"])
+        assert np.array_equal(r["hyp_ok"], g[f"hok{t}"]) and np.array_equal(r["hyp_count"], g[f"hcnt{t}"])
+        assert np.array_equal(r["inliers"], g[f"inl{t}"])
+        assert np.abs(r["tr"] - g[f"tr{t}"]).max() < 1e-9
+        if r["ok"]:
+            ok, pose = oracle.pose_update(pose, r["tr"])
+            assert ok and np.abs(pose - g["poses"][n_pose]).max() < 1e-9
+            n_pose += 1
+    assert n_pose == len(g["poses"])
+    # stress cases: truncation (found > K), the mono configuration (general F + ratio test), index-0 terminator, ties
+    def sp(enforce_epipolar, Fm, sampson, second, ratio, K, radius):
+        m = oracle.match_params_temporal()
+        m.enforce_epipolar, m.enforce_2nd_best, m.max_neighbors = int(enforce_epipolar), int(second), K
+        m.radius, m.sampson_thresh, m.ratio_2nd_best = radius, sampson, ratio
+        if Fm is not None:
+            for i, v in enumerate(np.asarray(Fm).reshape(9)):
+                m.F[i] = v
+        return m
+    cases = {"trunc": sp(False, None, 0.0, True, .9, 16, 80.0),
+             "mono": sp(True, g["s_Fg"], 50.0, True, .9, 250, 10.0),
+             "plain": sp(False, None, 0.0, False, .9, 250, 80.0)}
+    for name, m in cases.items():
+        o = oracle.match_desc(g["s_kpa"], g["s_kpb"], g["s_da"], g["s_db"], m)
+        _dense_matches(o, g[f"s_{name}_dense"])
+        assert np.array_equal(o["matches"], oracle.sort_matches(g[f"s_{name}_push"]))
+        assert o["valid"].sum() >= (1 if name == "mono" else 10), name
