@@ -327,4 +327,4 @@ def test_path_against_cv2_transcription(oracle):
         o = oracle.match_desc(g["s_kpa"], g["s_kpb"], g["s_da"], g["s_db"], m)
         _dense_matches(o, g[f"s_{name}_dense"])
         assert np.array_equal(o["matches"], oracle.sort_matches(g[f"s_{name}_push"]))
-        assert o["valid"].sum() >= (1 if name == "mono" else 10), name
+        assert (o["idx"] >= 0).sum() > 10, name   # (random descriptors: the ratio test rejects most)
