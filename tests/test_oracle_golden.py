@@ -321,7 +321,7 @@ def test_path_against_cv2_transcription(oracle):
                 m.F[i] = v
         return m
     cases = {"trunc": sp(False, None, 0.0, True, .9, 16, 80.0),
-             "mono": sp(True, g["s_Fg"], 50.0, True, .9, 250, 10.0),
+             "mono": sp(True, g["s_Fg"], 400.0, True, .9, 250, 25.0),
              "plain": sp(False, None, 0.0, False, .9, 250, 80.0)}
     for name, m in cases.items():
         o = oracle.match_desc(g["s_kpa"], g["s_kpb"], g["s_da"], g["s_db"], m)

@@ -327,8 +327,8 @@ def main():
     Fg = rng.standard_normal((3, 3))
     cases = {
         "trunc": dict(temporal, max_neighbors=16),
-        "mono": dict(enforce_epipolar=True, F=Fg, sampson_thresh=50.0, enforce_2nd_best=True, ratio_2nd_best=.9,
-                     max_neighbors=250, radius=10.0),
+        "mono": dict(enforce_epipolar=True, F=Fg, sampson_thresh=400.0, enforce_2nd_best=True, ratio_2nd_best=.9,
+                     max_neighbors=250, radius=25.0),
         "plain": dict(temporal, enforce_2nd_best=False),
     }
     out["s_kpa"], out["s_kpb"], out["s_da"], out["s_db"], out["s_Fg"] = kpa, kpb, da, db, Fg
