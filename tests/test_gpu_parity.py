@@ -552,3 +552,47 @@ def test_long_sequence_properties(ctx, api, oracle, small_sequence):
     assert_tr_close(rec["tr"][:12], o["records"]["tr"])
     poses = api.chain_poses(rec)
     assert len(poses) == F and np.isfinite(poses).all()
+
+
+def test_chunk_upload_equals_per_frame_upload(ctx, api, small_sequence):
+    """viso_seq_upload_chunk_images (three large copies per chunk, keypoint rows padded to the sequence capacity) gives
+    the same records as frame-by-frame uploads"""
+    from libviso_b200 import synth
+    frames, _ = small_sequence
+    P1, P2 = synth.kitti_calib()
+    F, H = len(frames), 30
+    seeds = make_seeds(F, H)
+    pg = api.param_default(ransac_iter=H)
+    cap = max(max(len(f["kpL"]), len(f["kpR"])) for f in frames)
+
+    def fresh():
+        seq = ctx.sequence(F, cap, 121, H)
+        seq.set_calib(P1, P2)
+        seq.set_image_size(synth.W, synth.H)
+        seq.set_seeds(seeds, H)
+        return seq
+
+    a = fresh()
+    a.upload_images(frames)
+    a.run(pg)
+    want = a.download()
+    a.close()
+
+    b = fresh()
+    capq = b.capacity()
+    assert capq >= cap
+    img = np.zeros((F, 2, synth.H, synth.W), np.uint8)
+    kpL = np.full((F, capq, 2), -7.0, np.float32); kpR = np.full((F, capq, 2), -7.0, np.float32)   # padding is ignored
+    nL = np.zeros(F, np.int32); nR = np.zeros(F, np.int32)
+    for t, f in enumerate(frames):
+        img[t, 0], img[t, 1] = f["imL"], f["imR"]
+        nL[t], nR[t] = len(f["kpL"]), len(f["kpR"])
+        kpL[t, :nL[t]] = f["kpL"]; kpR[t, :nR[t]] = f["kpR"]
+    for t0, t1 in ((0, 4), (4, F)):
+        b.upload_chunk_images_raw(t0, t1 - t0, img[t0:].ctypes.data, kpL[t0:].ctypes.data, nL[t0:].ctypes.data,
+                                  kpR[t0:].ctypes.data, nR[t0:].ctypes.data)
+        ctx.sync()          # pageable numpy memory
+        b.run_range(pg, t0, t1)
+    got = b.download()
+    b.close()
+    assert got.tobytes() == want.tobytes()
