@@ -398,8 +398,8 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "sad_match_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args), "peak_source": peak_src,
-                         "note": "HBM fraction as the contract defines it; the kernel is bound by the L1 data pipe (71% of peak "
-                                 "wavefronts) and the ALU pipe (53%), not by HBM: see DESIGN.md section 4",
+                         "note": "HBM fraction as the contract defines it; the kernel is bound by the L1 data pipe (66% of peak "
+                                 "wavefronts in the committed ncu capture) and the ALU pipe (51%), not by HBM: DESIGN.md section 4",
                          "algorithmic_bytes_per_launch": int(match_bytes), "kernel_ms": mm,
                          "sad_pairs_per_launch": int(sad_pairs), "sad_evaluated_per_launch": int(sad_eval),
                          "kernel_share_of_step": mm / (dev_ms / args.steps)},
