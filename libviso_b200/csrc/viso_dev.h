@@ -30,8 +30,12 @@
 #ifndef VISO_MATCH_MINB
 #define VISO_MATCH_MINB 8          /* resident CTAs per SM the match kernels are compiled for */
 #endif
+#ifndef VISO_TILE_W
 #define VISO_TILE_W 6            /* query tile of sad_match: 6 x 4 cells = 96 x 64 px */
+#endif
+#ifndef VISO_TILE_H
 #define VISO_TILE_H 4
+#endif
 #define VISO_STRIP_QPC 16         /* queries per CTA of the generic match kernel */
 #define VISO_PENDING (-2)         /* dense result .w: left by the tile kernel for the generic kernel */
 #define VISO_MAX_REG_ROWS 64     /* grid rows a staged tile neighbourhood may span */
