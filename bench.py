@@ -46,7 +46,7 @@ def parse_args():
                     help="distinct rendered frames; the sequence drives back and forth over them (every frame has "
                          "its own HBM copy, so the working set is the full --frames)")
     ap.add_argument("--cpu-pairs", type=int, default=96, help="frame pairs in the cpu_baseline sample")
-    ap.add_argument("--chunk", type=int, default=200, help="frames per upload/compute chunk of the e2e pipeline")
+    ap.add_argument("--chunk", type=int, default=125, help="frames per upload/compute chunk of the e2e pipeline")
     ap.add_argument("--input", default="images", choices=["images", "descriptors"],
                     help="what crosses the boundary per frame: the two 8-bit images + keypoints (descriptors extracted "
                          "on the device, viso.cpp:1004-1024) or the reference's n x 121 f32 descriptor matrices")

@@ -333,7 +333,11 @@ int viso_seq_upload_chunk_images(viso_seq* s, int t0, int count, const uint8_t* 
     if (rc) return rc;
     cudaStream_t st = ctx->copy_stream;
     const size_t cap = s->cap, bytes = (size_t)s->img_w * s->img_h;
-    CK(cudaMemcpyAsync(s->imgL + 2 * (size_t)t0 * bytes, images, 2 * (size_t)count * bytes, cudaMemcpyHostToDevice, st));
+    /* pieces of ~16 MB: measured 54 GB/s against 36 GB/s for one 1 GB copy (tools/h2d_probe.py) */
+    const size_t total = 2 * (size_t)count * bytes, piece = (size_t)16 << 20;
+    for (size_t off = 0; off < total; off += piece)
+        CK(cudaMemcpyAsync(s->imgL + 2 * (size_t)t0 * bytes + off, images + off, std::min(piece, total - off),
+                           cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->kpL + (size_t)t0 * cap, kpL, (size_t)count * cap * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->kpR + (size_t)t0 * cap, kpR, (size_t)count * cap * 8, cudaMemcpyHostToDevice, st));
     for (int i = 0; i < count; ++i) {
