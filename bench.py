@@ -47,6 +47,8 @@ def parse_args():
                          "its own HBM copy, so the working set is the full --frames)")
     ap.add_argument("--cpu-pairs", type=int, default=96, help="frame pairs in the cpu_baseline sample")
     ap.add_argument("--chunk", type=int, default=125, help="frames per upload/compute chunk of the e2e pipeline")
+    ap.add_argument("--e2e-buffers", type=int, default=2, choices=[1, 2],
+                    help="sequence objects (each on its own context / streams) taking alternate e2e steps")
     ap.add_argument("--input", default="images", choices=["images", "descriptors"],
                     help="what crosses the boundary per frame: the two 8-bit images + keypoints (descriptors extracted "
                          "on the device, viso.cpp:1004-1024) or the reference's n x 121 f32 descriptor matrices")
@@ -212,7 +214,8 @@ def workload_config(args):
             "l2": "inputs larger than L2 (every frame has its own HBM copy: ~3 GB per sequence vs 126 MB L2)",
             "input": ("two 8-bit images + keypoints per frame, descriptors extracted on the device (viso.cpp:1004-1024)"
                       if args.input == "images" else "keypoints + n x 121 f32 descriptor matrices per frame (cv::Mat layout)"),
-            "e2e_pipeline": f"chunks of {args.chunk} frames: H2D on a copy stream overlapped with the previous chunk's kernels",
+            "e2e_pipeline": (f"chunks of {args.chunk} frames: H2D on a copy stream overlapped with the previous chunk's kernels; "
+                             f"{args.e2e_buffers} sequence object(s) on separate contexts take alternate steps"),
             "parallelism": f"{args.gpus} independent sequence(s), one per GPU, NCCL gather of 64-byte records"}
 
 
@@ -347,32 +350,65 @@ def main():
                 nL_host[t] = p["nL"]; nR_host[t] = p["nR"]
             img_b, kp_b = 2 * synth.H * synth.W, capq * 8
 
-        def e2e_step():
-            # chunked pipeline: the uploads of chunk k+1 (copy stream) overlap the kernels of chunk k
-            ctx._ck(api.lib().viso_seq_set_seeds(seq.h, api._p(seeds_pin.data_ptr()), H))
-            for t0 in range(0, F, args.chunk):
+        # Two sequence objects on two contexts (each with its own compute and copy streams) take alternate steps, so the
+        # tail of step k (the kernels of its last chunk, the record read-back) overlaps the uploads of step k+1 and
+        # the PCIe link never idles.  Every step still uploads all of its inputs and reads its own records back inside
+        # the timed region (the read-back of step k is issued after step k+1 has been enqueued).
+        lanes = [(ctx, seq)]
+        if args.e2e_buffers > 1:
+            ctx2 = api.Context(local_rank)
+            ctx2.set_image_extent(synth.W, synth.H)
+            seq2 = ctx2.sequence(F, cap, 121, H)
+            seq2.set_calib(P1, P2)
+            if use_img:
+                seq2.set_image_size(synth.W, synth.H)
+            lanes.append((ctx2, seq2))
+        rec_pins = [rec_pin] + [torch.zeros(F * 16, dtype=torch.int32).pin_memory() for _ in lanes[1:]]
+
+        def enqueue(i):
+            c, sq = lanes[i % len(lanes)]
+            c._ck(api.lib().viso_seq_set_seeds(sq.h, api._p(seeds_pin.data_ptr()), H))
+            for t0 in range(0, F, args.chunk):   # chunked pipeline: uploads of chunk k+1 overlap the kernels of chunk k
                 t1 = min(F, t0 + args.chunk)
                 if use_img:
-                    seq.upload_chunk_images_raw(t0, t1 - t0, img_host.data_ptr() + t0 * img_b, kpL_host.data_ptr() + t0 * kp_b,
-                                                nL_host.data_ptr() + 4 * t0, kpR_host.data_ptr() + t0 * kp_b,
-                                                nR_host.data_ptr() + 4 * t0)
+                    sq.upload_chunk_images_raw(t0, t1 - t0, img_host.data_ptr() + t0 * img_b, kpL_host.data_ptr() + t0 * kp_b,
+                                               nL_host.data_ptr() + 4 * t0, kpR_host.data_ptr() + t0 * kp_b,
+                                               nR_host.data_ptr() + 4 * t0)
                 else:
-                    upload_range(t0, t1)
-                seq.run_range(param, t0, t1)
-            seq.download_raw(rec_pin.data_ptr())
-        for _ in range(2):
-            e2e_step()
+                    p0 = sq
+                    for t in range(t0, t1):
+                        p = pinned[order[t]]
+                        p0.upload_frame_raw(t, p["kpL"].data_ptr(), p["nL"], p["kpR"].data_ptr(), p["nR"],
+                                            p["dL"].data_ptr(), p["dR"].data_ptr())
+                sq.run_range(param, t0, t1)
+
+        def collect(i):
+            lanes[i % len(lanes)][1].download_raw(rec_pins[i % len(lanes)].data_ptr())   # synchronises that lane only
+
+        def e2e_run(n):
+            for i in range(n):
+                enqueue(i)
+                if i >= len(lanes) - 1:
+                    collect(i - (len(lanes) - 1))
+            for i in range(max(0, n - (len(lanes) - 1)), n):
+                collect(i)
+
+        e2e_run(2 * len(lanes))
+        for c, _ in lanes:
+            c.sync()
         barrier()
         t0 = time.perf_counter()
-        ctx.timer_begin()
-        for _ in range(args.steps):
-            e2e_step()
-        e2e_ms = ctx.timer_end()
-        e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
-        e2e_ms = max(e2e_ms, e2e_wall_ms)  # the download synchronises every step; report the slower clock
+        e2e_run(args.steps)
+        for c, _ in lanes:
+            c.sync()
+        e2e_ms = 1e3 * (time.perf_counter() - t0)   # host clock around fully synchronised work on both lanes
         barrier()
-        rec_e2e = np.frombuffer(rec_pin.numpy().tobytes(), dtype=api.RECORD_DTYPE)
-        assert rec_e2e.tobytes() == rec.tobytes(), "e2e records differ from the resident run"
+        for rp in rec_pins:
+            rec_e2e = np.frombuffer(rp.numpy().tobytes(), dtype=api.RECORD_DTYPE)
+            assert rec_e2e.tobytes() == rec.tobytes(), "e2e records differ from the resident run"
+        for c2, s2 in lanes[1:]:
+            s2.close()
+            c2.close()
 
     clocks = sampler.stop()  # sampled over both timed regions (device-resident and end-to-end)
 
