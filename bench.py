@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=125, help="frames per upload/compute chunk of the e2e pipeline")
     ap.add_argument("--e2e-buffers", type=int, default=2, choices=[1, 2],
                     help="sequence objects (each on its own context / streams) taking alternate e2e steps")
-    ap.add_argument("--input", default="images", choices=["images", "descriptors"],
+    ap.add_argument("--input", default="images", choices=["images", "descriptors", "raw"],
                     help="what crosses the boundary per frame: the two 8-bit images + keypoints (descriptors extracted "
                          "on the device, viso.cpp:1004-1024) or the reference's n x 121 f32 descriptor matrices")
     ap.add_argument("--no-cpu", action="store_true")
@@ -212,8 +212,9 @@ def workload_config(args):
             "frames": args.frames, "features": args.features, "ransac_iter": args.hyp,
             "unique_rendered_frames": min(args.unique, args.frames),
             "l2": "inputs larger than L2 (every frame has its own HBM copy: ~3 GB per sequence vs 126 MB L2)",
-            "input": ("two 8-bit images + keypoints per frame, descriptors extracted on the device (viso.cpp:1004-1024)"
-                      if args.input == "images" else "keypoints + n x 121 f32 descriptor matrices per frame (cv::Mat layout)"),
+            "input": {"images": "two 8-bit images + keypoints per frame, descriptors extracted on the device (viso.cpp:1004-1024)",
+                      "raw": "two 8-bit images per frame; Harris detector (viso.cpp:925-976) and descriptors on the device",
+                      "descriptors": "keypoints + n x 121 f32 descriptor matrices per frame (cv::Mat layout)"}[args.input],
             "e2e_pipeline": (f"chunks of {args.chunk} frames: H2D on a copy stream overlapped with the previous chunk's kernels; "
                              f"{args.e2e_buffers} sequence object(s) on separate contexts take alternate steps"),
             "parallelism": f"{args.gpus} independent sequence(s), one per GPU, NCCL gather of 64-byte records"}
@@ -276,9 +277,12 @@ def main():
     param = api.param_default(ransac_iter=H)
 
     # pinned host copies of the unique frames (the e2e path uploads from these every step)
-    use_img = args.input == "images"
+    use_img = args.input in ("images", "raw")
+    use_raw = args.input == "raw"   # images only: keypoints detected on the device as well (viso.cpp:925-976)
     if use_img:
         seq.set_image_size(synth.W, synth.H)
+    if use_raw:
+        seq.set_detector(args.features)
     pinned = []
     for f in frames:
         p = {}
@@ -293,7 +297,9 @@ def main():
     def upload_range(t0, t1):
         for t in range(t0, t1):
             p = pinned[order[t]]
-            if use_img:
+            if use_raw:
+                seq.upload_frame_raw_ptr(t, p["imL"].data_ptr(), p["imR"].data_ptr())
+            elif use_img:
                 seq.upload_frame_images_raw(t, p["imL"].data_ptr(), p["imR"].data_ptr(), p["kpL"].data_ptr(), p["nL"],
                                             p["kpR"].data_ptr(), p["nR"])
             else:
@@ -303,7 +309,9 @@ def main():
     def upload_all():
         upload_range(0, F)
 
-    if use_img:  # keypoint rows are uploaded padded to the sequence capacity
+    if use_raw:
+        h2d = F * 2 * synth.W * synth.H + seeds.nbytes
+    elif use_img:  # keypoint rows are uploaded padded to the sequence capacity
         h2d = F * (2 * synth.W * synth.H + 2 * seq.capacity() * 8) + seeds.nbytes
     else:
         h2d = sum((pinned[i]["nL"] + pinned[i]["nR"]) * (8 + 121 * 4) for i in order) + seeds.nbytes
@@ -362,6 +370,8 @@ def main():
             seq2.set_calib(P1, P2)
             if use_img:
                 seq2.set_image_size(synth.W, synth.H)
+            if use_raw:
+                seq2.set_detector(args.features)
             lanes.append((ctx2, seq2))
         rec_pins = [rec_pin] + [torch.zeros(F * 16, dtype=torch.int32).pin_memory() for _ in lanes[1:]]
 
@@ -370,7 +380,9 @@ def main():
             c._ck(api.lib().viso_seq_set_seeds(sq.h, api._p(seeds_pin.data_ptr()), H))
             for t0 in range(0, F, args.chunk):   # chunked pipeline: uploads of chunk k+1 overlap the kernels of chunk k
                 t1 = min(F, t0 + args.chunk)
-                if use_img:
+                if use_raw:
+                    sq.upload_chunk_raw(t0, t1 - t0, img_host.data_ptr() + t0 * img_b)
+                elif use_img:
                     sq.upload_chunk_images_raw(t0, t1 - t0, img_host.data_ptr() + t0 * img_b, kpL_host.data_ptr() + t0 * kp_b,
                                                nL_host.data_ptr() + 4 * t0, kpR_host.data_ptr() + t0 * kp_b,
                                                nR_host.data_ptr() + 4 * t0)

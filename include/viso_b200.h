@@ -188,6 +188,33 @@ int viso_seq_upload_frame_images(viso_seq* seq, int t, const uint8_t* imgL, cons
 int viso_seq_capacity(const viso_seq* seq);
 int viso_seq_upload_chunk_images(viso_seq* seq, int t0, int count, const uint8_t* images, const float* kpL,
                                  const int32_t* nL, const float* kpR, const int32_t* nR);
+/* Detector on the device: HarrisBinnedFeatureDetector::detectImpl, reference src/viso.cpp:911-979
+ * (cv::cornerHarris(block 3, aperture 5, k, BORDER_DEFAULT); nbinx x nbiny bins of (width/nbinx) x (height/nbiny)
+ * pixels; per bin the n_features/(nbinx*nbiny) largest |response| != 0; bins concatenated binx outer, biny inner).
+ * cornerHarris is float32 with a rounding OpenCV does not define (FMA use differs between its vector body and tail
+ * columns, its box filter keeps running sums that depend on the stripe split), so the response is evaluated in ONE
+ * canonical order, float32, no fused multiply-adds, every border BORDER_REFLECT_101:
+ *   s = 1/(16*3*255) in double; f0,f1,f2 = (float)(6s), (float)(4s), (float)(1s)
+ *   r(x,y) = (p[x+2]-p[x-2]) + 2(p[x+1]-p[x-1]);   Dx = f0*r(y); Dx += f1*(r(y-1)+r(y+1)); Dx += f2*(r(y-2)+r(y+2))
+ *   t(x,y) = f0*p[x]; t += f1*(p[x-1]+p[x+1]); t += f2*(p[x-2]+p[x+2]);   Dy = 2*(t(y+1)-t(y-1)); Dy += t(y+2)-t(y-2)
+ *   a,b,c = 3x3 sums of Dx*Dx, Dx*Dy, Dy*Dy: rows (c[x-1]+c[x])+c[x+1], then (rs[y-1]+rs[y])+rs[y+1]
+ *   response = (a*c - b*b) - (k*(a+c))*(a+c)
+ * (within 2e-6 of the image maximum of cv2.cornerHarris; on the synthetic frames the kept keypoints are the same).
+ * Inside a bin the kept keypoints are the largest by (|response|, x, y), emitted ascending -- std::nth_element leaves
+ * an implementation-defined order there.  The reference never initialises its k (viso.cpp:915-919); 0.04f is its
+ * constructor's default argument.
+ *   viso_detect_harris: one image from host memory (rows `pitch` bytes apart) -> kp_xy (up to n_features rows of x, y),
+ *   kp_response (nullable), *n_out.
+ *   viso_seq_set_detector + viso_seq_upload_frame_raw / viso_seq_upload_chunk_raw: the sequence object detects and
+ *   describes on the device, only the 8-bit images are uploaded (viso_seq_set_image_size first; n_features rounded
+ *   down to a multiple of the bin count must not exceed the sequence's max_kp).
+ *   viso_seq_get_keypoints: the keypoints of frame t, side 0 (left) / 1 (right), after a run. */
+int viso_detect_harris(viso_ctx* ctx, const uint8_t* img, int width, int height, int pitch, int n_features, int nbinx,
+                       int nbiny, float k, float* kp_xy, float* kp_response, int32_t* n_out);
+int viso_seq_set_detector(viso_seq* seq, int n_features, int nbinx, int nbiny, float k);
+int viso_seq_upload_frame_raw(viso_seq* seq, int t, const uint8_t* imgL, const uint8_t* imgR);
+int viso_seq_upload_chunk_raw(viso_seq* seq, int t0, int count, const uint8_t* images);
+int viso_seq_get_keypoints(viso_seq* seq, int t, int side, float* kp_xy, int32_t* n);
 /* Uploads run on a dedicated copy stream.  viso_seq_run_range() orders itself after every upload enqueued so far and
  * enqueues the pipeline for frames [t0, t1) (frame pairs (t-1, t) for t in [max(t0,1), t1); frame t0-1 must have been
  * run before), so uploading chunk k+1 from pinned memory overlaps the kernels of chunk k. */

@@ -233,6 +233,15 @@ class Context:
         self._ck(lib().viso_solve_rigid_motion(self.h, _p(A), _p(B), A.shape[1], _p(T)))
         return T
 
+    # ---- HarrisBinnedFeatureDetector::detectImpl, viso.cpp:925-976 ----
+    def detect_harris(self, img, n_features, nbinx=24, nbiny=5, k=0.04, with_response=False):
+        img = np.ascontiguousarray(img, dtype=np.uint8); h, w = img.shape
+        xy = np.zeros((max(n_features, 1), 2), np.float32); rs = np.zeros(max(n_features, 1), np.float32)
+        n = C.c_int32(0)
+        self._ck(lib().viso_detect_harris(self.h, _p(img), w, h, w, int(n_features), int(nbinx), int(nbiny), C.c_float(k),
+                                          _p(xy), _p(rs), C.byref(n)))
+        return (xy[:n.value].copy(), rs[:n.value].copy()) if with_response else xy[:n.value].copy()
+
     # ---- match_circle, viso.cpp:206-243 ----
     def match_circle(self, mlr, mlrp, m11, m22):
         mlr, mlrp, m11, m22 = (_i32(a).reshape(-1, 3) for a in (mlr, mlrp, m11, m22))
@@ -368,6 +377,27 @@ class Sequence:
     def upload_images(self, frames):
         for t, f in enumerate(frames):
             self.upload_frame_images(t, f["imL"], f["imR"], f["kpL"], f["kpR"])
+
+    # ---- device detector + extractor: only the images are uploaded ----
+    def set_detector(self, n_features, nbinx=24, nbiny=5, k=0.04):
+        self.ctx._ck(lib().viso_seq_set_detector(self.h, int(n_features), int(nbinx), int(nbiny), C.c_float(k)))
+
+    def upload_frame_raw_images(self, t, imL, imR):
+        imL, imR = np.ascontiguousarray(imL, dtype=np.uint8), np.ascontiguousarray(imR, dtype=np.uint8)
+        self.ctx._ck(lib().viso_seq_upload_frame_raw(self.h, int(t), _p(imL), _p(imR)))
+        self.ctx.sync()  # the numpy temporaries are pageable and may die
+
+    def upload_frame_raw_ptr(self, t, imL_ptr, imR_ptr):
+        self.ctx._ck(lib().viso_seq_upload_frame_raw(self.h, int(t), _p(imL_ptr), _p(imR_ptr)))
+
+    def upload_chunk_raw(self, t0, count, images_ptr):
+        """count frames in one block from (pinned) host memory: images [count][2][H][W] u8"""
+        self.ctx._ck(lib().viso_seq_upload_chunk_raw(self.h, int(t0), int(count), _p(images_ptr)))
+
+    def get_keypoints(self, t, side):
+        out = np.zeros((self.max_kp + 32, 2), np.float32); n = C.c_int32(0)
+        self.ctx._ck(lib().viso_seq_get_keypoints(self.h, int(t), int(side), _p(out), C.byref(n)))
+        return out[:n.value].copy()
 
     def run_range(self, param, t0, t1):
         self.ctx._ck(lib().viso_seq_run_range(self.h, C.byref(param), int(t0), int(t1)))

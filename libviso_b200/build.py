@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libviso_b200.so")
-SOURCES = ["match.cu", "sort_circle.cu", "estimation.cu", "geometry.cu", "capi.cu", "capi_seq.cu"]
+SOURCES = ["detect.cu", "match.cu", "sort_circle.cu", "estimation.cu", "geometry.cu", "capi.cu", "capi_seq.cu"]
 HEADERS = [os.path.join(CSRC, "viso_dev.h"), os.path.join(CSRC, "introsort.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "capi_internal.h"),
            os.path.join(os.path.dirname(HERE), "include", "viso_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-O3", "-std=c++17",

@@ -129,6 +129,25 @@ double host_det4(const double M[16])
     return r;
 }
 
+int make_harris_cfg(viso_ctx* ctx, int width, int height, int pitch, int n_features, int nbinx, int nbiny, float k,
+                    HarrisCfg* out)
+{
+    if (width < 8 || height < 8 || pitch < width) return ctx->fail(VISO_ERR_ARG, "detector: images must be at least 8 x 8");
+    if (nbinx < 1 || nbiny < 1 || n_features < 0) return ctx->fail(VISO_ERR_ARG, "detector: bad bin counts"); /* viso.cpp:919 */
+    HarrisCfg c{};
+    c.w = width; c.h = height; c.pitch = pitch; c.nbinx = nbinx; c.nbiny = nbiny;
+    c.sx = width / nbinx; c.sy = height / nbiny;                         /* viso.cpp:932-933 */
+    if (c.sx < 1 || c.sy < 1) return ctx->fail(VISO_ERR_ARG, "detector: more bins than pixels (viso.cpp:934)");
+    c.per = n_features / (nbinx * nbiny);                                /* viso.cpp:943 */
+    c.k = k;
+    const double sc = 1.0 / ((double)(1 << 4) * 3 * 255.0);              /* cornerHarris: aperture 5, block 3, 8-bit */
+    c.f0 = (float)(6.0 * sc); c.f1 = (float)(4.0 * sc); c.f2 = (float)(1.0 * sc);
+    if ((size_t)c.sx * c.sy > 65535 || viso_harris_smem(c) > 200 * 1024)
+        return ctx->fail(VISO_ERR_DOMAIN, "detector: a bin may hold at most ~33000 pixels (its responses are kept in shared memory)");
+    *out = c;
+    return VISO_OK;
+}
+
 } // namespace viso_capi
 using namespace viso_capi;
 
@@ -918,6 +937,54 @@ int viso_chain_poses(const viso_record* records, int n_frames, double* poses)
         ++np;
     }
     return np;
+}
+
+/* ------------------------------------------------------------------------------------------------ detector */
+
+int viso_detect_harris(viso_ctx* ctx, const uint8_t* img, int width, int height, int pitch, int n_features, int nbinx,
+                       int nbiny, float k, float* kp_xy, float* kp_response, int32_t* n_out)
+{
+    if (!ctx) return VISO_ERR_ARG;
+    if (!img || !kp_xy || !n_out) return ctx->fail(VISO_ERR_ARG, "detect_harris: null argument");
+    HarrisCfg c;
+    int rc = make_harris_cfg(ctx, width, height, pitch, n_features, nbinx, nbiny, k, &c);
+    if (rc) return rc;
+    *n_out = 0;
+    if (c.per == 0) return VISO_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)nbinx * nbiny, slots = nb * c.per;
+    struct Bufs { unsigned char* img; float2 *kp, *tmp; float *resp, *resp_tmp; int *n, *bin_count, *flag; DetectJob* job; } b;
+    auto carve = [&](Carver& cv) {
+        b.img = cv.take<unsigned char>((size_t)pitch * height);
+        b.kp = cv.take<float2>(slots); b.tmp = cv.take<float2>(slots);
+        b.resp = cv.take<float>(slots); b.resp_tmp = cv.take<float>(slots);
+        b.n = cv.take<int>(1); b.bin_count = cv.take<int>(nb); b.flag = cv.take<int>(1);
+        b.job = cv.take<DetectJob>(1);
+    };
+    Carver measure(nullptr);
+    carve(measure);
+    rc = ensure_scratch(ctx, measure.off);
+    if (rc) return rc;
+    Carver real(ctx->d_scr);
+    carve(real);
+    cudaStream_t s = ctx->stream;
+    const int one = 1;
+    const DetectJob job{b.img, b.kp, b.n, b.tmp, b.resp_tmp, b.resp, b.bin_count, b.flag};
+    CK(cudaMemcpyAsync(b.img, img, (size_t)pitch * height, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.flag, &one, 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.job, &job, sizeof(job), cudaMemcpyHostToDevice, s));
+    CK(viso_launch_detect(b.job, 1, c, s));
+    ctx->launches += 2;
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, b.n, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(kp_xy, b.kp, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        if (kp_response) CK(cudaMemcpyAsync(kp_response, b.resp, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    *n_out = n;
+    return VISO_OK;
 }
 
 } /* extern "C" */

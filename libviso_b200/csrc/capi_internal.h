@@ -47,6 +47,9 @@ namespace viso_capi {
 ParamDev make_param_dev(const viso_param* p);
 MatchParamsDev make_match_dev(const viso_match_params* p);
 int status_from_flags(viso_ctx* ctx, int flags);
+/* validates the detector geometry and fills the launch configuration; 0 or a VISO_ERR_* with ctx->err set */
+int make_harris_cfg(viso_ctx* ctx, int width, int height, int pitch, int n_features, int nbinx, int nbiny, float k,
+                    HarrisCfg* out);
 } // namespace viso_capi
 
 #endif

@@ -44,8 +44,16 @@ struct viso_seq {
     unsigned char *imgL = nullptr, *imgR = nullptr;
     int img_w = 0, img_h = 0;
     ExtractJob* extract_jobs = nullptr;
+    /* device detector (viso_seq_set_detector) */
+    DetectJob* detect_jobs = nullptr;
+    float2* kp_tmp = nullptr;
+    int *bin_count = nullptr, *detect = nullptr, *h_detect = nullptr;
+    HarrisCfg hc{};
+    bool det_set = false;
+    int det_n = 0;                        /* keypoints per image at most: per * nbins */
     cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
     int run_hi = 0;                       /* frames [0, run_hi) may still be read by enqueued kernels */
+    int run_hi_total = 0;                 /* frames [0, run_hi_total) have been through the pipeline at least once */
     std::vector<RansacProb> h_probs;
     int H_cur = -1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -117,13 +125,14 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     SA(pack_jobs, 2 * F); SA(grid_jobs, 2 * F); SA(match_jobs, 3 * F); SA(sort_jobs, F); SA(circ_jobs, F); SA(probs, F);
     SA(pairs, 2); SA(err, 1); SA(pending, 1); SA(from_image, F); SA(extract_jobs, 2 * F);
 #undef SA
-    if (cudaMallocHost(&s->h_nL, 3 * F * sizeof(int)) != cudaSuccess) {
+    if (cudaMallocHost(&s->h_nL, 4 * F * sizeof(int)) != cudaSuccess) {
         seq_free(s);
         return ctx->fail(VISO_ERR_NOMEM, "seq_create: cudaMallocHost failed");
     }
     s->h_nR = s->h_nL + F;
     s->h_from_image = s->h_nL + 2 * F;
-    std::memset(s->h_nL, 0, 3 * F * sizeof(int));
+    s->h_detect = s->h_nL + 3 * F;
+    std::memset(s->h_nL, 0, 4 * F * sizeof(int));
     cudaStream_t st = ctx->stream;
     auto bail = [&](cudaError_t e, const char* what) { seq_free(s); return ctx->fail_cuda(e, what); };
     cudaError_t e;
@@ -257,6 +266,7 @@ int viso_seq_upload_frame(viso_seq* s, int t, const float* kpL, int nL, const fl
     s->h_nL[t] = nL;
     s->h_nR[t] = nR;
     s->h_from_image[t] = 0;
+    s->h_detect[t] = 0;
     return VISO_OK;
 }
 
@@ -313,6 +323,7 @@ int viso_seq_upload_frame_images(viso_seq* s, int t, const uint8_t* imgL, const 
     s->h_nL[t] = nL;
     s->h_nR[t] = nR;
     s->h_from_image[t] = 1;
+    s->h_detect[t] = 0;
     return VISO_OK;
 }
 
@@ -344,6 +355,86 @@ int viso_seq_upload_chunk_images(viso_seq* s, int t0, int count, const uint8_t* 
         s->h_nL[t0 + i] = nL[i];
         s->h_nR[t0 + i] = nR[i];
         s->h_from_image[t0 + i] = 1;
+        s->h_detect[t0 + i] = 0;
+    }
+    return VISO_OK;
+}
+
+int viso_seq_set_detector(viso_seq* s, int n_features, int nbinx, int nbiny, float k)
+{
+    if (!s) return VISO_ERR_ARG;
+    viso_ctx* ctx = s->ctx;
+    if (!s->imgL) return ctx->fail(VISO_ERR_ARG, "seq_set_detector: viso_seq_set_image_size has not been called");
+    HarrisCfg c;
+    int rc = make_harris_cfg(ctx, s->img_w, s->img_h, s->img_w, n_features, nbinx, nbiny, k, &c);
+    if (rc) return rc;
+    const size_t nb = (size_t)nbinx * nbiny, slots = nb * c.per, F = s->F, cap = s->cap, bytes = (size_t)s->img_w * s->img_h;
+    if (slots < 1 || slots > cap) return ctx->fail(VISO_ERR_ARG, "seq_set_detector: n_features must be between the bin count and the sequence's max_kp");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!s->det_set || nb * c.per != (size_t)s->det_n || c.nbinx != s->hc.nbinx || c.nbiny != s->hc.nbiny) {
+        if (s->det_set) return ctx->fail(VISO_ERR_ARG, "seq_set_detector: the bin layout of a sequence object is fixed once set");
+        cudaError_t e;
+        if ((e = seq_alloc(s, &s->kp_tmp, 2 * F * slots)) != cudaSuccess || (e = seq_alloc(s, &s->bin_count, 2 * F * nb)) != cudaSuccess ||
+            (e = seq_alloc(s, &s->detect, F)) != cudaSuccess || (e = seq_alloc(s, &s->detect_jobs, 2 * F)) != cudaSuccess) {
+            ctx->err = std::string("seq_set_detector cudaMalloc: ") + cudaGetErrorString(e);
+            return e == cudaErrorMemoryAllocation ? VISO_ERR_NOMEM : VISO_ERR_CUDA;
+        }
+        std::vector<DetectJob> dj(2 * F);
+        for (size_t t = 0; t < F; ++t) {
+            dj[2 * t] = DetectJob{s->imgL + 2 * t * bytes, s->kpL + t * cap, s->nL + t, s->kp_tmp + 2 * t * slots, nullptr, nullptr,
+                                  s->bin_count + 2 * t * nb, s->detect + t};
+            dj[2 * t + 1] = DetectJob{s->imgR + 2 * t * bytes, s->kpR + t * cap, s->nR + t, s->kp_tmp + (2 * t + 1) * slots, nullptr,
+                                      nullptr, s->bin_count + (2 * t + 1) * nb, s->detect + t};
+        }
+        CK(cudaMemcpyAsync(s->detect_jobs, dj.data(), dj.size() * sizeof(DetectJob), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(s->detect, 0, F * 4, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    s->hc = c;
+    s->det_n = (int)slots;
+    s->det_set = true;
+    return VISO_OK;
+}
+
+int viso_seq_upload_frame_raw(viso_seq* s, int t, const uint8_t* imgL, const uint8_t* imgR)
+{
+    if (!s) return VISO_ERR_ARG;
+    viso_ctx* ctx = s->ctx;
+    if (!s->det_set) return ctx->fail(VISO_ERR_ARG, "seq_upload_frame_raw: viso_seq_set_detector has not been called");
+    if (t < 0 || t >= s->F || !imgL || !imgR) return ctx->fail(VISO_ERR_ARG, "seq_upload_frame_raw: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_guard(s, t);
+    if (rc) return rc;
+    cudaStream_t st = ctx->copy_stream;
+    const size_t bytes = (size_t)s->img_w * s->img_h;
+    CK(cudaMemcpyAsync(s->imgL + 2 * t * bytes, imgL, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->imgR + 2 * t * bytes, imgR, bytes, cudaMemcpyHostToDevice, st));
+    s->h_nL[t] = s->h_nR[t] = s->det_n;   /* upper bound for launch sizing; the kernels read the device-side counts */
+    s->h_from_image[t] = 1;
+    s->h_detect[t] = 1;
+    return VISO_OK;
+}
+
+int viso_seq_upload_chunk_raw(viso_seq* s, int t0, int count, const uint8_t* images)
+{
+    if (!s) return VISO_ERR_ARG;
+    viso_ctx* ctx = s->ctx;
+    if (!s->det_set) return ctx->fail(VISO_ERR_ARG, "seq_upload_chunk_raw: viso_seq_set_detector has not been called");
+    if (t0 < 0 || count < 1 || t0 + count > s->F || !images) return ctx->fail(VISO_ERR_ARG, "seq_upload_chunk_raw: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_guard(s, t0);
+    if (rc) return rc;
+    cudaStream_t st = ctx->copy_stream;
+    const size_t bytes = (size_t)s->img_w * s->img_h;
+    const size_t total = 2 * (size_t)count * bytes, piece = (size_t)16 << 20;
+    for (size_t off = 0; off < total; off += piece)
+        CK(cudaMemcpyAsync(s->imgL + 2 * (size_t)t0 * bytes + off, images + off, std::min(piece, total - off),
+                           cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < count; ++i) {
+        s->h_nL[t0 + i] = s->h_nR[t0 + i] = s->det_n;
+        s->h_from_image[t0 + i] = 1;
+        s->h_detect[t0 + i] = 1;
     }
     return VISO_OK;
 }
@@ -389,12 +480,14 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
     CK(cudaMemcpyAsync(s->nL + t0, s->h_nL + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->nR + t0, s->h_nR + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->from_image + t0, s->h_from_image + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    if (s->det_set) CK(cudaMemcpyAsync(s->detect + t0, s->h_detect + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
     if (t0 == 0) {
         CK(cudaMemsetAsync(s->pairs, 0, 16, st));
         CK(cudaMemsetAsync(s->err, 0, 4, st));
     }
-    int max_n = 0, max_nL = 0, any_img = 0, any_f32 = 0;
+    int max_n = 0, max_nL = 0, any_img = 0, any_f32 = 0, any_det = 0;
     for (int t = t0; t < t1; ++t) {
+        if (s->h_detect[t]) any_det = 1;
         max_n = std::max(max_n, std::max(s->h_nL[t], s->h_nR[t]));
         max_nL = std::max(max_nL, s->h_nL[t]);
         if (s->h_from_image[t]) any_img = 1; else any_f32 = 1;
@@ -413,6 +506,11 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
 
     int nl = 0;
     if (any_f32 && max_n > 0) { CK(viso_launch_pack(s->pack_jobs + 2 * t0, 2 * nf, max_n, s->dlen, s->err, st)); ++nl; }
+    if (any_det) {
+        /* overwrites the counts copied above with the detector's own */
+        CK(viso_launch_detect(s->detect_jobs + 2 * t0, 2 * nf, s->hc, st));
+        nl += 2;
+    }
     if (any_img && max_n > 0) {
         CK(viso_launch_extract(s->extract_jobs + 2 * t0, 2 * nf, max_n, s->img_w, s->img_h, s->img_w, 5, st));
         ++nl;
@@ -435,6 +533,7 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
     ctx->launches += nl;
     CK(cudaEventRecord(s->ev_compute, st));
     s->run_hi = std::max(s->run_hi, t1);
+    s->run_hi_total = std::max(s->run_hi_total, t1);
     s->have_ms = max_n > 0;
     s->ran = true;
     return VISO_OK;
@@ -474,11 +573,27 @@ int viso_seq_download(viso_seq* s, viso_record* records)
     return status_from_flags(ctx, flags);
 }
 
+/* frames whose keypoints were detected on the device: bring their counts to the host (getters, statistics) */
+static int refresh_counts(viso_seq* s)
+{
+    viso_ctx* ctx = s->ctx;
+    if (!s->det_set || !s->ran) return VISO_OK;
+    std::vector<int> n(2 * (size_t)s->F);
+    CK(cudaMemcpyAsync(n.data(), s->nL, (size_t)s->F * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(n.data() + s->F, s->nR, (size_t)s->F * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int t = 0; t < s->F; ++t)
+        if (s->h_detect[t] && t < s->run_hi_total) { s->h_nL[t] = n[t]; s->h_nR[t] = n[s->F + t]; }
+    return VISO_OK;
+}
+
 int viso_seq_stats(viso_seq* s, int64_t* match_bytes, int64_t* sad_pairs, int64_t* sad_evaluated)
 {
     if (!s) return VISO_ERR_ARG;
     viso_ctx* ctx = s->ctx;
     CK(cudaSetDevice(ctx->device));
+    int rcc = refresh_counts(s);
+    if (rcc) return rcc;
     if (match_bytes) {
         /* SURVEY 8d, per frame pair, fused, u16 layout: the four descriptor sets (rows of 256 B + 8 B of
          * coordinates) read once and three dense int4 outputs written */
@@ -518,6 +633,8 @@ int viso_seq_get_dense(viso_seq* s, int which, int t, int32_t* out4, int32_t* n)
     viso_ctx* ctx = s->ctx;
     if (t < 0 || t >= s->F || which < 0 || which > 2 || !out4 || !n) return ctx->fail(VISO_ERR_ARG, "seq_get_dense: bad argument");
     CK(cudaSetDevice(ctx->device));
+    int rcc = refresh_counts(s);
+    if (rcc) return rcc;
     const int cnt = which == 2 ? s->h_nR[t] : s->h_nL[t];
     const int4* src = (which == 0 ? s->dense_lr : which == 1 ? s->dense_11 : s->dense_22) + (size_t)t * s->cap;
     *n = cnt;
@@ -532,10 +649,28 @@ int viso_seq_get_packed(viso_seq* s, int t, int side, uint16_t* rows, int32_t* n
     viso_ctx* ctx = s->ctx;
     if (t < 0 || t >= s->F || side < 0 || side > 1 || !rows || !n) return ctx->fail(VISO_ERR_ARG, "seq_get_packed: bad argument");
     CK(cudaSetDevice(ctx->device));
+    int rcc = refresh_counts(s);
+    if (rcc) return rcc;
     const int cnt = side ? s->h_nR[t] : s->h_nL[t];
     const uint16_t* src = (side ? s->dRu : s->dLu) + (size_t)t * s->cap * VISO_DESC_U16;
     *n = cnt;
     if (cnt > 0) CK(cudaMemcpyAsync(rows, src, (size_t)cnt * VISO_DESC_U16 * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VISO_OK;
+}
+
+int viso_seq_get_keypoints(viso_seq* s, int t, int side, float* kp_xy, int32_t* n)
+{
+    if (!s) return VISO_ERR_ARG;
+    viso_ctx* ctx = s->ctx;
+    if (t < 0 || t >= s->F || side < 0 || side > 1 || !kp_xy || !n) return ctx->fail(VISO_ERR_ARG, "seq_get_keypoints: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    int rcc = refresh_counts(s);
+    if (rcc) return rcc;
+    const int cnt = side ? s->h_nR[t] : s->h_nL[t];
+    const float2* src = (side ? s->kpR : s->kpL) + (size_t)t * s->cap;
+    *n = cnt;
+    if (cnt > 0) CK(cudaMemcpyAsync(kp_xy, src, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return VISO_OK;
 }

@@ -87,6 +87,25 @@ struct ExtractJob {
     const int* from_image;    /* == 0: skip (descriptors were uploaded as f32 rows) */
 };
 
+/* HarrisBinnedFeatureDetector::detectImpl on the device (viso.cpp:925-976): 8-bit image -> keypoints */
+struct DetectJob {
+    const unsigned char* img; /* rows x pitch */
+    float2* kp;               /* out: keypoints, bins concatenated in the reference's order */
+    int* n;                   /* out: keypoint count */
+    float2* tmp;              /* [nbins][per] per-bin slots */
+    float* resp_tmp;          /* [nbins][per] |response| of the slots, or null */
+    float* resp;              /* out: |response| per keypoint (KeyPoint::response, viso.cpp:968), or null */
+    int* bin_count;           /* [nbins] */
+    const int* detect;        /* == 0: skip (keypoints were uploaded) */
+};
+
+struct HarrisCfg {
+    int w, h, pitch;
+    int nbinx, nbiny, sx, sy; /* bins and their size in pixels (w / nbinx, h / nbiny) */
+    int per;                  /* keypoints kept per bin */
+    float k, f0, f1, f2;      /* Harris k and the scaled 5-tap smoothing kernel (include/viso_b200.h) */
+};
+
 struct GridJob {
     const float2* xy;
     const int* n;
@@ -159,6 +178,8 @@ struct CircleJob {             /* per frame pair */
 cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dlen, int* err_flag, cudaStream_t s);
 cudaError_t viso_launch_extract(const ExtractJob* jobs, int n_jobs, int max_n, int width, int height, int pitch, int radius,
                                 cudaStream_t s);
+size_t viso_harris_smem(const HarrisCfg& c);
+cudaError_t viso_launch_detect(const DetectJob* jobs, int n_jobs, const HarrisCfg& c, cudaStream_t s);
 cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStream_t s);
 cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
                               GridCfg g, unsigned long long* sad_pairs, int* n_pending, cudaStream_t s, int* launches);

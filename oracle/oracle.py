@@ -298,6 +298,42 @@ def extract_descriptors(sob, kp, radius=5):
     return d
 
 
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def sobel_x(img):
+    img = _u8(img); h, w = img.shape
+    out = np.zeros((h, w), np.float32)
+    lib().vo_sobel_x(_p(img), h, w, _p(out))
+    return out
+
+
+def harris_response(img, k=0.04):
+    img = _u8(img); h, w = img.shape
+    out = np.zeros((h, w), np.float32)
+    lib().vo_harris_response(_p(img), h, w, C.c_float(k), _p(out))
+    return out
+
+
+def detect_harris_binned(img, n, nbinx=24, nbiny=5, k=0.04, order_rule=1, with_response=False):
+    img = _u8(img); h, w = img.shape
+    xy = np.zeros((max(n, 1), 2), np.float32); rs = np.zeros(max(n, 1), np.float32)
+    cnt = lib().vo_detect_harris_binned(_p(img), h, w, n, nbinx, nbiny, C.c_float(k), order_rule, _p(xy), _p(rs))
+    assert cnt >= 0
+    return (xy[:cnt].copy(), rs[:cnt].copy()) if with_response else xy[:cnt].copy()
+
+
+def frames_from_images(images, n_features=2040, k=0.04):
+    """images: list of (imL, imR) uint8.  The front end of viso.cpp:1208-1222: detect, then describe."""
+    frames = []
+    for imL, imR in images:
+        kpL = detect_harris_binned(imL, n_features, k=k); kpR = detect_harris_binned(imR, n_features, k=k)
+        frames.append(dict(kpL=kpL, kpR=kpR, dL=extract_descriptors(sobel_x(imL), kpL),
+                           dR=extract_descriptors(sobel_x(imR), kpR), imL=imL, imR=imR))
+    return frames
+
+
 def sequence(frames, P1, P2, param, seeds, dump=False):
     """frames: list of dict(kpL, kpR, dL, dR).  seeds: [n_frames, H, 3] uint32.
     Returns dict(records, poses, and (dump=True) lr_matches, lr_count, m11, m22, circ, inliers as per-frame lists)."""

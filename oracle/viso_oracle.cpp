@@ -638,6 +638,125 @@ void vo_extract_descriptors(const float* sob, int h, int w, const float* kp, int
     }
 }
 
+/* ---- front end: Sobel-x, Harris response, binned detector ---- */
+
+static inline int reflect101(int i, int n)
+{
+    /* cv::borderInterpolate(BORDER_REFLECT_101) for |overshoot| < n */
+    if (n == 1) return 0;
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+void vo_sobel_x(const uint8_t* img, int h, int w, float* sob)
+{
+    /* viso.cpp:1010: 3x3 Sobel, kx = [-1 0 1], ky = [1 2 1]; integers, exact in float */
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* r0 = img + (size_t)reflect101(y - 1, h) * w;
+        const uint8_t* r1 = img + (size_t)y * w;
+        const uint8_t* r2 = img + (size_t)reflect101(y + 1, h) * w;
+        for (int x = 0; x < w; ++x) {
+            const int xl = reflect101(x - 1, w), xr = reflect101(x + 1, w);
+            const int v = (r0[xr] - r0[xl]) + 2 * (r1[xr] - r1[xl]) + (r2[xr] - r2[xl]);
+            sob[(size_t)y * w + x] = (float)v;
+        }
+    }
+}
+
+void vo_harris_response(const uint8_t* img, int h, int w, float k, float* resp)
+{
+    /* see viso_oracle.h for the canonical operation order (cv::cornerHarris, viso.cpp:930) */
+    const double s = 1.0 / ((double)(1 << 4) * 3 * 255.0);
+    const float f0 = (float)(6.0 * s), f1 = (float)(4.0 * s), f2 = (float)(1.0 * s);
+    const size_t N = (size_t)h * w;
+    std::vector<float> r(N), t(N), xx(N), xy(N), yy(N), rsa(N), rsb(N), rsc(N);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* row = img + (size_t)y * w;
+            const float pl2 = row[reflect101(x - 2, w)], pl1 = row[reflect101(x - 1, w)], p0 = row[x],
+                        pr1 = row[reflect101(x + 1, w)], pr2 = row[reflect101(x + 2, w)];
+            r[(size_t)y * w + x] = (pr2 - pl2) + 2.0f * (pr1 - pl1);
+            float tt = f0 * p0;
+            tt = tt + f1 * (pl1 + pr1);
+            tt = tt + f2 * (pl2 + pr2);
+            t[(size_t)y * w + x] = tt;
+        }
+    for (int y = 0; y < h; ++y) {
+        const size_t ym2 = (size_t)reflect101(y - 2, h) * w, ym1 = (size_t)reflect101(y - 1, h) * w,
+                     yp1 = (size_t)reflect101(y + 1, h) * w, yp2 = (size_t)reflect101(y + 2, h) * w, y0 = (size_t)y * w;
+        for (int x = 0; x < w; ++x) {
+            float dx = f0 * r[y0 + x];
+            dx = dx + f1 * (r[ym1 + x] + r[yp1 + x]);
+            dx = dx + f2 * (r[ym2 + x] + r[yp2 + x]);
+            float dy = 2.0f * (t[yp1 + x] - t[ym1 + x]);
+            dy = dy + (t[yp2 + x] - t[ym2 + x]);
+            xx[y0 + x] = dx * dx; xy[y0 + x] = dx * dy; yy[y0 + x] = dy * dy;
+        }
+    }
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const size_t o = (size_t)y * w, l = o + reflect101(x - 1, w), c = o + x, rr = o + reflect101(x + 1, w);
+            rsa[c] = (xx[l] + xx[c]) + xx[rr];
+            rsb[c] = (xy[l] + xy[c]) + xy[rr];
+            rsc[c] = (yy[l] + yy[c]) + yy[rr];
+        }
+    for (int y = 0; y < h; ++y) {
+        const size_t u = (size_t)reflect101(y - 1, h) * w, o = (size_t)y * w, d = (size_t)reflect101(y + 1, h) * w;
+        for (int x = 0; x < w; ++x) {
+            const float a = (rsa[u + x] + rsa[o + x]) + rsa[d + x];
+            const float b = (rsb[u + x] + rsb[o + x]) + rsb[d + x];
+            const float c = (rsc[u + x] + rsc[o + x]) + rsc[d + x];
+            const float tr = a + c;
+            resp[o + x] = (a * c - b * b) - (k * tr) * tr;
+        }
+    }
+}
+
+int vo_detect_harris_binned(const uint8_t* img, int h, int w, int n, int nbinx, int nbiny, float k, int order_rule,
+                            float* kp_xy, float* kp_resp)
+{
+    /* viso.cpp:925-976 */
+    std::vector<float> resp((size_t)h * w);
+    vo_harris_response(img, h, w, k, resp.data());
+    const int stridex = w / nbinx, stridey = h / nbiny;               /* :932-933 */
+    if (stridex <= 0 || stridey <= 0) return -1;                       /* :934 assert */
+    struct elem {
+        int x, y; float val;
+        bool operator<(const elem& o) const { return val < o.val; }    /* :941 */
+    };
+    const int per = n / (nbinx * nbiny);                               /* :943 */
+    std::vector<elem> v;
+    v.reserve((size_t)stridex * stridey);
+    int out = 0;
+    for (int binx = 0; binx < nbinx; ++binx)
+        for (int biny = 0; biny < nbiny; ++biny) {
+            for (int x = binx * stridex; x < (binx + 1) * stridex && x < w; ++x)
+                for (int y = biny * stridey; y < (biny + 1) * stridey && y < h; ++y) {
+                    const float response = fabsf(resp[(size_t)y * w + x]);
+                    /* isEqual(response, 0.f), misc.cpp:10-15: |r - 0| <= 1e-6 |r|  <=>  r == 0 (NaN is kept) */
+                    if (fabsf(response - 0.0f) <= 1e-6f * fabsf(response)) continue;
+                    v.push_back(elem{x, y, response});
+                }
+            const int m = ((int)v.size() > per) ? (int)v.size() - per : 0; /* :961 */
+            if (order_rule == 0) {
+                if (m > 0) std::nth_element(v.begin(), v.begin() + m, v.end()); /* :963 */
+            } else {
+                std::sort(v.begin(), v.end(), [](const elem& a, const elem& b) {
+                    if (a.val != b.val) return a.val < b.val;
+                    if (a.x != b.x) return a.x < b.x;
+                    return a.y < b.y;
+                });
+            }
+            for (size_t i = m; i < v.size(); ++i, ++out) {
+                kp_xy[2 * out] = (float)v[i].x; kp_xy[2 * out + 1] = (float)v[i].y; /* :967 */
+                if (kp_resp) kp_resp[out] = v[i].val;
+            }
+            v.clear();
+        }
+    return out;
+}
+
 /* ---- lower-priority geometry; not bit-pinned: SVD vectors are unique only up to rounding ---- */
 
 static void jacobi_eig_sym(double* A, int n, double* V)

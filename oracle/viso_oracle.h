@@ -155,6 +155,38 @@ int vo_project_points(const double* X, int n, const double P[12], double* x);
 void vo_extract_descriptors(const float* sob, int h, int w, const float* kp, int n, int radius, float* d);
 
 /*
+ * Front end.
+ *
+ * vo_sobel_x: cv::Sobel(image, CV_32F, 1, 0, 3, 1, 0, BORDER_DEFAULT) (viso.cpp:1010) -- integer valued, bit-exact
+ * against cv2 (tests/golden/sobel.npz).
+ *
+ * vo_harris_response: cv::cornerHarris(image, block 3, aperture 5, k, BORDER_DEFAULT) (viso.cpp:930) for 8-bit input.
+ * cornerHarris is a float32 pipeline whose rounding is NOT defined by OpenCV (FMA use differs between the vector body
+ * and the tail columns, the box filter keeps running sums whose order depends on the stripe split), so this is the
+ * CANONICAL float32 evaluation both the oracle and the device follow, no fused multiply-adds, operations in this order:
+ *   s = 1/(2^(aperture-1) * block * 255) in double; f0,f1,f2 = (float)(6s), (float)(4s), (float)(1s)
+ *   r(x,y) = (p[x+2]-p[x-2]) + 2(p[x+1]-p[x-1])           (exact), pixels reflected (BORDER_REFLECT_101)
+ *   Dx = f0*r(y); Dx += f1*(r(y-1)+r(y+1)); Dx += f2*(r(y-2)+r(y+2))
+ *   t(x,y) = f0*p[x]; t += f1*(p[x-1]+p[x+1]); t += f2*(p[x-2]+p[x+2])
+ *   Dy = 2*(t(y+1)-t(y-1)); Dy += (t(y+2)-t(y-2))
+ *   xx = Dx*Dx, xy = Dx*Dy, yy = Dy*Dy; box: rs = (c[x-1]+c[x])+c[x+1]; S = (rs[y-1]+rs[y])+rs[y+1], the covariance
+ *   images reflected (BORDER_REFLECT_101 on positions, as cv::boxFilter does)
+ *   response = (a*c - b*b) - (k*(a+c))*(a+c)
+ * Checked against cv2.cornerHarris to 1e-6 of the image maximum (tests/test_oracle_golden.py); parity with the
+ * reference for this function is therefore "within float rounding", not bit-exact -- the device is bit-exact with THIS.
+ *
+ * vo_detect_harris_binned: HarrisBinnedFeatureDetector::detectImpl (viso.cpp:925-976): per bin (binx outer, biny inner)
+ * the n/(nbinx*nbiny) largest |response| != 0.  order_rule 0: literally std::nth_element on the scan-ordered vector
+ * (libstdc++ introselect; the order of the kept elements is whatever it leaves); order_rule 1: canonical -- kept set =
+ * largest by (|response|, x, y), emitted ascending by that key (the rule the device implements; same SET as rule 0
+ * whenever no two responses tie at the cut).  kp_xy: up to n rows of (x, y); returns the keypoint count.
+ */
+void vo_sobel_x(const uint8_t* img, int h, int w, float* sob);
+void vo_harris_response(const uint8_t* img, int h, int w, float k, float* resp);
+int vo_detect_harris_binned(const uint8_t* img, int h, int w, int n, int nbinx, int nbiny, float k, int order_rule,
+                            float* kp_xy, float* kp_resp /* nullable */);
+
+/*
  * Whole-sequence pipeline, viso.cpp:1205-1327 minus detection/description/debug output.
  * Frame t has nL[t]/nR[t] keypoints starting at row offL[t]/offR[t] of kpL/kpR (x,y float) and dL/dR (dlen floats/row).
  * seeds: [n_frames][H][3] uint32 sample seeds (frame 0's block unused).

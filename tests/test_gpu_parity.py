@@ -596,3 +596,72 @@ def test_chunk_upload_equals_per_frame_upload(ctx, api, small_sequence):
     got = b.download()
     b.close()
     assert got.tobytes() == want.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------ detector (8f rank 2)
+
+@pytest.mark.gpu
+def test_detect_harris_matches_oracle(ctx, oracle, small_sequence):
+    """viso_detect_harris against the oracle's canonical cornerHarris + binned top-n: keypoints, their order and their
+    responses bit-for-bit.  Cases: KITTI geometry, odd sizes with borders inside bins, quotas above the number of
+    columns (no lower bound from the column maxima) and above 256 candidates (bisection), flat regions (bins with
+    fewer non-zero responses than the quota), ties (a periodic pattern gives many equal responses)."""
+    frames, _ = small_sequence
+    rng = np.random.default_rng(5)
+    cases = [(frames[0]["imL"], 2040, 24, 5), (frames[1]["imR"], 600, 24, 5), (frames[2]["imL"], 24 * 5 * 166, 24, 5),
+             (frames[3]["imL"], 24 * 5 * 300, 24, 5),
+             (rng.integers(0, 256, size=(83, 97), dtype=np.uint8), 60, 4, 3),
+             (rng.integers(0, 256, size=(64, 200), dtype=np.uint8), 50, 1, 1),      # one 200-px-wide bin: 4 strips
+             (rng.integers(0, 256, size=(150, 16), dtype=np.uint8), 30, 1, 2)]
+    flat = np.full((90, 120), 90, np.uint8); flat[20:26, 30:37] = 250; flat[60:70, 80:95] = 10
+    cases.append((flat, 12 * 40, 4, 3))
+    yy, xx = np.mgrid[0:96, 0:128]
+    cases.append(((((xx // 8) + (yy // 8)) % 2 * 200 + 20).astype(np.uint8), 8 * 30, 4, 2))   # checkerboard: ties
+    for img, n, nx, ny in cases:
+        want, wresp = oracle.detect_harris_binned(img, n, nx, ny, 0.04, order_rule=1, with_response=True)
+        got, gresp = ctx.detect_harris(img, n, nx, ny, 0.04, with_response=True)
+        assert len(got) == len(want), (img.shape, n, len(got), len(want))
+        assert np.array_equal(got, want), (img.shape, n)
+        assert gresp.tobytes() == wresp.tobytes(), (img.shape, n)
+
+
+@pytest.mark.gpu
+def test_sequence_from_raw_images(ctx, api, oracle, small_sequence):
+    """images only: detector + extractor + pipeline on the device against the oracle's front end + pipeline"""
+    from libviso_b200 import synth
+    frames, _ = small_sequence
+    P1, P2 = synth.kitti_calib()
+    H, nfeat = 50, 600
+    seeds = make_seeds(len(frames), H)
+    oframes = oracle.frames_from_images([(f["imL"], f["imR"]) for f in frames], nfeat)
+    po = oracle.param_default(ransac_iter=H)
+    o = oracle.sequence(oframes, P1, P2, po, seeds, dump=True)
+    pg = api.param_default(ransac_iter=H)
+    seq = ctx.sequence(len(frames), nfeat, 121, H)
+    seq.set_calib(P1, P2)
+    seq.set_image_size(synth.W, synth.H)
+    seq.set_detector(nfeat)
+    seq.set_seeds(seeds, H)
+    # frames 0-1 in one block, the rest frame by frame, two submissions
+    block = np.ascontiguousarray(np.stack([np.stack([frames[t]["imL"], frames[t]["imR"]]) for t in range(2)]))
+    seq.upload_chunk_raw(0, 2, block)
+    ctx.sync()
+    seq.run_range(pg, 0, 2)
+    for t in range(2, len(frames)):
+        seq.upload_frame_raw_images(t, frames[t]["imL"], frames[t]["imR"])
+    seq.run_range(pg, 2, len(frames))
+    rec = seq.download()
+    for t, f in enumerate(oframes):
+        assert np.array_equal(seq.get_keypoints(t, 0), f["kpL"]) and np.array_equal(seq.get_keypoints(t, 1), f["kpR"])
+        if t > 0:
+            assert np.array_equal(seq.get_dense(1, t), o["m11"][t]), t
+    for k in ("ok", "n_inliers", "n_circ", "best_hyp"):
+        assert np.array_equal(rec[k], o["records"][k]), k
+    assert_tr_close(rec["tr"], o["records"]["tr"])
+    assert rec["ok"][1:].all() and (rec["n_inliers"][1:] > 50).all()
+    # mixing: frame 3 re-uploaded with host keypoints (the oracle's), same result
+    f = oframes[3]
+    seq.upload_frame_images(3, f["imL"], f["imR"], f["kpL"], f["kpR"])
+    seq.run(pg)
+    assert seq.download().tobytes() == rec.tobytes()
+    seq.close()

@@ -328,3 +328,74 @@ def test_path_against_cv2_transcription(oracle):
         _dense_matches(o, g[f"s_{name}_dense"])
         assert np.array_equal(o["matches"], oracle.sort_matches(g[f"s_{name}_push"]))
         assert (o["idx"] >= 0).sum() > 10, name   # (random descriptors: the ratio test rejects most)
+
+
+# ------------------------------------------------------------------------------------------------ front end (8f rank 1-2)
+
+def _harris_numpy(img, k=np.float32(0.04)):
+    """the canonical float32 evaluation of oracle/viso_oracle.h written with numpy (IEEE, no FMA)"""
+    def refl(i, n):
+        i = np.where(i < 0, -i, i)
+        return np.where(i >= n, 2 * (n - 1) - i, i)
+    h, w = img.shape
+    p = img.astype(np.float32)
+    xi = lambda d: refl(np.arange(w) + d, w)
+    yi = lambda d: refl(np.arange(h) + d, h)
+    s = 1.0 / (16 * 3 * 255.0)
+    f0, f1, f2 = np.float32(6.0 * s), np.float32(4.0 * s), np.float32(1.0 * s)
+    r = (p[:, xi(2)] - p[:, xi(-2)]) + np.float32(2) * (p[:, xi(1)] - p[:, xi(-1)])
+    dx = f0 * r; dx = dx + f1 * (r[yi(-1)] + r[yi(1)]); dx = dx + f2 * (r[yi(-2)] + r[yi(2)])
+    t = f0 * p; t = t + f1 * (p[:, xi(-1)] + p[:, xi(1)]); t = t + f2 * (p[:, xi(-2)] + p[:, xi(2)])
+    dy = np.float32(2) * (t[yi(1)] - t[yi(-1)]); dy = dy + (t[yi(2)] - t[yi(-2)])
+    def box(c):
+        rs = (c[:, xi(-1)] + c) + c[:, xi(1)]
+        return (rs[yi(-1)] + rs) + rs[yi(1)]
+    a, b, c = box(dx * dx), box(dx * dy), box(dy * dy)
+    tr = a + c
+    return (a * c - b * b) - (k * tr) * tr
+
+
+@pytest.mark.parametrize("case", ["crop", "noise"])
+def test_harris_response_and_detector_against_opencv(oracle, case):
+    """tests/golden/harris.npz: cv2.cornerHarris (not bit-reproducible, see oracle/viso_oracle.h) within 2e-6 of the
+    image maximum; the canonical evaluation bit-exactly against its numpy statement; the binned detector run on the
+    oracle's response picks the keypoints cv2's response picks"""
+    g = load("harris.npz")
+    img, ref = g[case + "_img"], g[case + "_resp"]
+    nx, ny, n = (int(v) for v in g[case + "_bins"])
+    r = oracle.harris_response(img, 0.04)
+    assert np.abs(r - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.array_equal(r, _harris_numpy(img))
+    kp, resp = oracle.detect_harris_binned(img, n, nx, ny, 0.04, order_rule=1, with_response=True)
+    assert len(kp) == n
+    assert np.array_equal(resp, np.abs(r)[kp[:, 1].astype(int), kp[:, 0].astype(int)])
+    want = set(map(tuple, g[case + "_kp"]))
+    got = set(map(tuple, kp))
+    assert len(got & want) >= 0.95 * len(want)
+    # the reference's literal std::nth_element (order_rule 0) keeps the same set; only the order inside a bin differs
+    kp0 = oracle.detect_harris_binned(img, n, nx, ny, 0.04, order_rule=0)
+    assert set(map(tuple, kp0)) == got
+    per = n // (nx * ny)
+    for b in range(nx * ny):
+        blk, blk0 = kp[b * per:(b + 1) * per], kp0[b * per:(b + 1) * per]
+        assert set(map(tuple, blk)) == set(map(tuple, blk0))
+        sx, sy = img.shape[1] // nx, img.shape[0] // ny
+        assert (blk[:, 0] // sx == b // ny).all() and (blk[:, 1] // sy == b % ny).all()   # binx outer, biny inner
+        assert (np.diff(resp[b * per:(b + 1) * per]) >= 0).all()                          # ascending inside a bin
+
+
+def test_harris_detector_edge_cases(oracle):
+    """flat image: every response is 0 and is skipped (viso.cpp:956); bins with fewer candidates than the quota"""
+    flat = np.full((40, 48), 100, np.uint8)
+    assert len(oracle.detect_harris_binned(flat, 24, 4, 2)) == 0
+    img = flat.copy()
+    img[10:14, 5:9] = 255           # one corner blob in the first bin
+    kp = oracle.detect_harris_binned(img, 8 * 400, 4, 2)     # quota 400 per bin, far more than non-zero responses
+    assert 0 < len(kp) < 8 * 400 and (kp[:, 0] < 24).all() and (kp[:, 1] < 24).all()
+    r = np.abs(oracle.harris_response(img))
+    assert len(kp) == int((r[:40, :48] != 0).sum())
+
+
+def test_sobel_x_matches_opencv(oracle):
+    g = load("sobel.npz")
+    assert np.array_equal(oracle.sobel_x(g["img"]), g["sob"])

@@ -111,9 +111,40 @@ def sobel_case():
     np.savez_compressed(os.path.join(OUT, "sobel.npz"), img=img, sob=sob)
 
 
+def harris_case():
+    """cv::cornerHarris(image, 3, 5, 0.04, BORDER_DEFAULT) (viso.cpp:930) on a crop of a synthetic frame plus a random
+    image, and the binned detector (viso.cpp:925-976, canonical order rule) applied to cv2's response.  cornerHarris is
+    not bit-reproducible (see oracle/viso_oracle.h): the oracle is compared with a tolerance."""
+    from libviso_b200 import synth
+    tex = synth.make_texture(77, 1024)
+    R = np.eye(3); pos = np.array([0.0, 0.0, 0.0])
+    full = synth.render(R, pos, tex, np.random.default_rng(78))
+    rng = np.random.default_rng(14)
+    out = {}
+    for name, img, (nx, ny, n) in (("crop", np.ascontiguousarray(full[100:220, 300:460]), (4, 3, 96)),
+                                   ("noise", rng.integers(0, 256, size=(75, 102), dtype=np.uint8), (2, 1, 40))):
+        resp = cv2.cornerHarris(img, 3, 5, 0.04, borderType=cv2.BORDER_DEFAULT)
+        out[name + "_img"] = img
+        out[name + "_resp"] = resp
+        out[name + "_bins"] = np.array([nx, ny, n], np.int32)
+        a = np.abs(resp); h, w = img.shape; sx, sy = w // nx, h // ny; per = n // (nx * ny)
+        kps = []
+        for bx in range(nx):
+            for by in range(ny):
+                blk = a[by * sy:(by + 1) * sy, bx * sx:(bx + 1) * sx]
+                vals = blk.T.reshape(-1); xs = np.repeat(np.arange(sx), sy) + bx * sx; ys = np.tile(np.arange(sy), sx) + by * sy
+                nz = vals != 0
+                vals, xs, ys = vals[nz], xs[nz], ys[nz]
+                o = np.lexsort((ys, xs, vals))[-per:]
+                kps.append(np.stack([xs[o], ys[o]], 1))
+        out[name + "_kp"] = np.concatenate(kps).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "harris.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     flann_cases()
     linalg_cases()
+    harris_case()
     sobel_case()
     print("wrote", sorted(os.listdir(OUT)))
