@@ -142,7 +142,7 @@ int make_harris_cfg(viso_ctx* ctx, int width, int height, int pitch, int n_featu
     c.k = k;
     const double sc = 1.0 / ((double)(1 << 4) * 3 * 255.0);              /* cornerHarris: aperture 5, block 3, 8-bit */
     c.f0 = (float)(6.0 * sc); c.f1 = (float)(4.0 * sc); c.f2 = (float)(1.0 * sc);
-    if ((size_t)c.sx * c.sy > 65535 || viso_harris_smem(c) > 200 * 1024)
+    if (viso_harris_cells(c) > 65535 || viso_harris_smem(c) > 200 * 1024)
         return ctx->fail(VISO_ERR_DOMAIN, "detector: a bin may hold at most ~33000 pixels (its responses are kept in shared memory)");
     *out = c;
     return VISO_OK;

@@ -18,12 +18,29 @@
 #include "viso_dev.h"
 #include "common.cuh"
 
+#ifndef HARRIS_WARPS
 #define HARRIS_WARPS 2
+#endif
 #define HARRIS_MAXIMA 256        /* column-segment maxima used for the lower bound of the cut value */
 #define HARRIS_STRIP 58          /* response columns per warp strip */
 #define HARRIS_DIRECT 256        /* candidate lists longer than this are first cut by bisection on the value */
+#ifndef HARRIS_AHEAD
+#define HARRIS_AHEAD 3           /* pixel rows requested ahead of the row being processed */
+#endif
+#ifndef HARRIS_UNROLL
+#define HARRIS_UNROLL 5          /* = the Sobel window height: the window shift becomes register renaming */
+#endif
+#define HARRIS_PRAGMA_(x) _Pragma(#x)
+#define HARRIS_PRAGMA(x) HARRIS_PRAGMA_(x)
 
 namespace {
+
+/* column stride of the response array: the rows padded to whole warp segments, odd so that the two-column lanes of a
+ * warp spread over 16 banks (an even stride would put them on 4 or 8) */
+__host__ __device__ __forceinline__ int harris_col_stride(int sy)
+{
+    return (((sy + HARRIS_WARPS - 1) / HARRIS_WARPS) * HARRIS_WARPS) | 1;
+}
 
 __device__ __forceinline__ int reflect_clamp(int i, int n)
 {
@@ -38,7 +55,9 @@ struct Tri { float a, b, c; };   /* xx, xy, yy (or their sums) */
 struct WalkState {
     float r0[5], r1[5], t0[5], t1[5];
     Tri prev0, prev1, cur0, cur1;
-    float p0, p1, n0, n1;        /* pixels of the current row and the two rows after it (requested early) */
+    float p0[HARRIS_AHEAD], p1[HARRIS_AHEAD];   /* pixels of the current row and the rows after it (requested early) */
+    const unsigned char* pf;                    /* fast rows: the pixel (row to request next, first column) */
+    unsigned* vp;                               /* fast rows: where the next response of the first column goes */
 };
 
 struct WalkLane {
@@ -46,15 +65,24 @@ struct WalkLane {
     bool left0, left1, right0, right1, valid0, valid1;
 };
 
-/* one pixel row enters the windows.  MODE 0: Sobel row pass only; 1: + covariance row yi-2; 2: + response row yi-3 */
-template <int MODE, bool BORDER>
+/* One pixel row enters the windows.  MODE 0: Sobel row pass only; 1: + covariance row yi-2; 2: + response row yi-3.
+ * GENERAL rows handle everything (reflected rows and columns, rows past the segment); the others are rows whose
+ * 64 x (5 + HARRIS_AHEAD) pixel neighbourhood is inside the image and whose response row is inside the bin (see
+ * harris_bin_kernel): running pointers, no selects, no masks. */
+template <int MODE, bool GENERAL>
 __device__ __forceinline__ void walk_row(WalkState& w, const WalkLane& ln, const unsigned char* __restrict__ img,
-                                         const HarrisCfg& c, int yi, int y0, int rb, unsigned* vcol, unsigned& best)
+                                         const HarrisCfg& c, int yi, int y0, int rb, int sp, unsigned* vcol, unsigned& best)
 {
-    /* the row two below is requested before this row's arithmetic */
-    const unsigned char* nrow = img + (size_t)reflect_clamp(yi + 2, c.h) * c.pitch;
-    const float q0 = __ldg(nrow + ln.lx0), q1 = __ldg(nrow + ln.lx1);
-    const float p0 = w.p0, p1 = w.p1;
+    /* a row further down is requested before this row's arithmetic */
+    float q0, q1;
+    if (GENERAL) {
+        const unsigned char* nrow = img + (size_t)reflect_clamp(yi + HARRIS_AHEAD, c.h) * c.pitch;
+        q0 = __ldg(nrow + ln.lx0); q1 = __ldg(nrow + ln.lx1);
+    } else {
+        q0 = __ldg(w.pf); q1 = __ldg(w.pf + 1);
+        w.pf += c.pitch;
+    }
+    const float p0 = w.p0[0], p1 = w.p1[0];
     const float L0 = __shfl_up_sync(FULL, p0, 1), L1 = __shfl_up_sync(FULL, p1, 1);
     const float R0 = __shfl_down_sync(FULL, p0, 1), R1 = __shfl_down_sync(FULL, p1, 1);
 #pragma unroll
@@ -63,7 +91,9 @@ __device__ __forceinline__ void walk_row(WalkState& w, const WalkLane& ln, const
     w.r1[4] = (R1 - L1) + 2.0f * (R0 - p0);
     float t = c.f0 * p0; t = t + c.f1 * (L1 + p1); t = t + c.f2 * (L0 + R0); w.t0[4] = t;
     t = c.f0 * p1; t = t + c.f1 * (p0 + R0); t = t + c.f2 * (L1 + R1); w.t1[4] = t;
-    w.p0 = w.n0; w.p1 = w.n1; w.n0 = q0; w.n1 = q1;
+#pragma unroll
+    for (int i = 0; i + 1 < HARRIS_AHEAD; ++i) { w.p0[i] = w.p0[i + 1]; w.p1[i] = w.p1[i + 1]; }
+    w.p0[HARRIS_AHEAD - 1] = q0; w.p1[HARRIS_AHEAD - 1] = q1;
     if (MODE == 0) return;
     float dx0 = c.f0 * w.r0[2]; dx0 = dx0 + c.f1 * (w.r0[1] + w.r0[3]); dx0 = dx0 + c.f2 * (w.r0[0] + w.r0[4]);
     float dx1 = c.f0 * w.r1[2]; dx1 = dx1 + c.f1 * (w.r1[1] + w.r1[3]); dx1 = dx1 + c.f2 * (w.r1[0] + w.r1[4]);
@@ -73,7 +103,7 @@ __device__ __forceinline__ void walk_row(WalkState& w, const WalkLane& ln, const
     Tri l{__shfl_up_sync(FULL, m1.a, 1), __shfl_up_sync(FULL, m1.b, 1), __shfl_up_sync(FULL, m1.c, 1)};
     Tri r{__shfl_down_sync(FULL, m0.a, 1), __shfl_down_sync(FULL, m0.b, 1), __shfl_down_sync(FULL, m0.c, 1)};
     Tri lm1 = m0, rm0 = m1;
-    if (BORDER) {
+    if (GENERAL) {
         if (ln.left0) l = m1;        /* covariance column -1 is column 1 (BORDER_REFLECT_101 of cv::boxFilter) */
         if (ln.right1) r = m0;       /* column w is column w-2 */
         if (ln.left1) lm1 = r;
@@ -82,28 +112,34 @@ __device__ __forceinline__ void walk_row(WalkState& w, const WalkLane& ln, const
     Tri new0{(l.a + m0.a) + rm0.a, (l.b + m0.b) + rm0.b, (l.c + m0.c) + rm0.c};
     Tri new1{(lm1.a + m1.a) + r.a, (lm1.b + m1.b) + r.b, (lm1.c + m1.c) + r.c};
     const int yc = yi - 2;
-    if (yc == c.h) { new0 = w.prev0; new1 = w.prev1; }   /* covariance row h is row h-2 (uniform branch) */
+    if (GENERAL && yc == c.h) { new0 = w.prev0; new1 = w.prev1; }   /* covariance row h is row h-2 */
     if (MODE == 2) {
         const int yr = yc - 1;
-        if (yr == 0) { w.prev0 = new0; w.prev1 = new1; }   /* row -1 is row 1 (uniform branch) */
+        if (GENERAL && yr == 0) { w.prev0 = new0; w.prev1 = new1; }   /* row -1 is row 1 */
         const float a0 = (w.prev0.a + w.cur0.a) + new0.a, b0 = (w.prev0.b + w.cur0.b) + new0.b, c0 = (w.prev0.c + w.cur0.c) + new0.c;
         const float a1 = (w.prev1.a + w.cur1.a) + new1.a, b1 = (w.prev1.b + w.cur1.b) + new1.b, c1 = (w.prev1.c + w.cur1.c) + new1.c;
         const float tr0 = a0 + c0, tr1 = a1 + c1;
         const float h0 = (a0 * c0 - b0 * b0) - (c.k * tr0) * tr0;
         const float h1 = (a1 * c1 - b1 * b1) - (c.k * tr1) * tr1;
         const unsigned v0 = __float_as_uint(h0) & 0x7fffffffu, v1 = __float_as_uint(h1) & 0x7fffffffu;
-        if (ln.valid0 && yr < rb) { vcol[yr - y0] = v0; best = max(best, v0); }
-        if (ln.valid1 && yr < rb) { vcol[c.sy + yr - y0] = v1; best = max(best, v1); }
+        if (GENERAL) {
+            if (ln.valid0 && yr < rb) { vcol[yr - y0] = v0; best = max(best, v0); }
+            if (ln.valid1 && yr < rb) { vcol[sp + yr - y0] = v1; best = max(best, v1); }
+        } else {
+            if (ln.valid0) { w.vp[0] = v0; best = max(best, v0); }
+            if (ln.valid1) { w.vp[sp] = v1; best = max(best, v1); }
+            ++w.vp;
+        }
     }
     w.prev0 = w.cur0; w.prev1 = w.cur1; w.cur0 = new0; w.cur1 = new1;
 }
 
 /* responses of rows [ra, min(ra + rows, rb)) x strip columns, written (as the bit pattern of |response|) into vals in
- * scan order; returns the largest value this lane produced.  Every trip count depends on `rows` only, which is the
- * same for all warps of the CTA: the compiler can then prove the shuffles convergent. */
-template <bool BORDER>
+ * scan order (column stride sp >= rows of the bin); returns the largest value this lane produced.  Every trip count
+ * (rows, nfast) is the same for all warps of the CTA: the compiler can then prove the shuffles convergent. */
 __device__ __forceinline__ unsigned harris_walk(const unsigned char* __restrict__ img, const HarrisCfg& c, int x0, int y0,
-                                                int xs, int ncol, int ra, int rb, int rows, unsigned* vals, int lane)
+                                                int xs, int ncol, int ra, int rb, int rows, int nfast, int sp,
+                                                unsigned* vals, int lane)
 {
     const int cbase = x0 + xs - 3;
     const int q0 = 2 * lane, cx0 = cbase + q0, cx1 = cx0 + 1;
@@ -111,7 +147,7 @@ __device__ __forceinline__ unsigned harris_walk(const unsigned char* __restrict_
     ln.lx0 = reflect_clamp(cx0, c.w); ln.lx1 = reflect_clamp(cx1, c.w);
     ln.left0 = cx0 == 0; ln.left1 = cx1 == 0; ln.right0 = cx0 == c.w - 1; ln.right1 = cx1 == c.w - 1;
     ln.valid0 = q0 >= 3 && q0 < 3 + ncol; ln.valid1 = q0 + 1 >= 3 && q0 + 1 < 3 + ncol;
-    unsigned* vcol = vals + (xs + q0 - 3) * c.sy;      /* the reference's scan order: x outer, y inner */
+    unsigned* vcol = vals + (xs + q0 - 3) * sp;        /* the reference's scan order: x outer, y inner */
     WalkState w;
 #pragma unroll
     for (int i = 0; i < 5; ++i) { w.r0[i] = w.r1[i] = w.t0[i] = w.t1[i] = 0.f; }
@@ -120,16 +156,24 @@ __device__ __forceinline__ unsigned harris_walk(const unsigned char* __restrict_
     /* pixel rows ra-3 .. : four rows fill the Sobel window, covariance rows ra-1 and ra fill the box window (for
      * ra == 0 "row -1" is computed from reflected pixels and then replaced by row 1, see walk_row) */
     int yi = ra - 3;
-    const unsigned char* row = img + (size_t)reflect_clamp(yi, c.h) * c.pitch;
-    w.p0 = __ldg(row + ln.lx0); w.p1 = __ldg(row + ln.lx1);
-    row = img + (size_t)reflect_clamp(yi + 1, c.h) * c.pitch;
-    w.n0 = __ldg(row + ln.lx0); w.n1 = __ldg(row + ln.lx1);
 #pragma unroll
-    for (int i = 0; i < 4; ++i, ++yi) walk_row<0, BORDER>(w, ln, img, c, yi, y0, rb, vcol, best);
+    for (int i = 0; i < HARRIS_AHEAD; ++i) {
+        const unsigned char* row = img + (size_t)reflect_clamp(yi + i, c.h) * c.pitch;
+        w.p0[i] = __ldg(row + ln.lx0); w.p1[i] = __ldg(row + ln.lx1);
+    }
 #pragma unroll
-    for (int i = 0; i < 2; ++i, ++yi) walk_row<1, BORDER>(w, ln, img, c, yi, y0, rb, vcol, best);
-#pragma unroll 5
-    for (int i = 0; i < rows; ++i, ++yi) walk_row<2, BORDER>(w, ln, img, c, yi, y0, rb, vcol, best);
+    for (int i = 0; i < 4; ++i, ++yi) walk_row<0, true>(w, ln, img, c, yi, y0, rb, sp, vcol, best);
+#pragma unroll
+    for (int i = 0; i < 2; ++i, ++yi) walk_row<1, true>(w, ln, img, c, yi, y0, rb, sp, vcol, best);
+    /* response rows: the first one may be image row 0 (general), then nfast rows without any special case */
+    walk_row<2, true>(w, ln, img, c, yi, y0, rb, sp, vcol, best);
+    ++yi;
+    w.pf = img + (size_t)max(yi + HARRIS_AHEAD, 0) * c.pitch + ln.lx0;
+    w.vp = vcol + (yi - 3 - y0);
+HARRIS_PRAGMA(unroll HARRIS_UNROLL)
+    for (int i = 0; i < nfast; ++i, ++yi) walk_row<2, false>(w, ln, img, c, yi, y0, rb, sp, vcol, best);
+#pragma unroll 1
+    for (int i = 1 + nfast; i < rows; ++i, ++yi) walk_row<2, true>(w, ln, img, c, yi, y0, rb, sp, vcol, best);
     return best;
 }
 
@@ -139,19 +183,22 @@ harris_bin_kernel(const DetectJob* __restrict__ jobs, HarrisCfg c)
     extern __shared__ unsigned smem_u[];
     const DetectJob job = jobs[blockIdx.y];
     if (*job.detect == 0) return;
-    const int npx = c.sx * c.sy;
+    const int sp = harris_col_stride(c.sy);
+    const int npx = c.sx * sp;
     unsigned* vals = smem_u;
     const int npx4 = (npx + 3) & ~3;
     unsigned* mx = vals + npx4;
     unsigned short* cand = reinterpret_cast<unsigned short*>(mx + HARRIS_MAXIMA);
     __shared__ int s_ncand, s_count;
     __shared__ unsigned s_cut, s_max;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = HARRIS_WARPS * 32, nw = HARRIS_WARPS;
     const int bin = blockIdx.x, binx = bin / c.nbiny, biny = bin % c.nbiny;
     const int x0 = binx * c.sx, y0 = biny * c.sy;
 
     for (int i = tid; i < HARRIS_MAXIMA; i += nt) mx[i] = 0;
     if (tid < npx4 - npx) vals[npx + tid] = 0;
+    /* the pad rows of the columns (sp - sy of them) are never written */
+    for (int i = tid; i < c.sx * (sp - c.sy); i += nt) vals[(i / (sp - c.sy)) * sp + c.sy + i % (sp - c.sy)] = 0;
     if (tid == 0) { s_ncand = 0; s_cut = 0; s_max = 0; }
     __syncthreads();
     /* strip by strip; the warps split a strip's rows evenly */
@@ -159,10 +206,13 @@ harris_bin_kernel(const DetectJob* __restrict__ jobs, HarrisCfg c)
     for (int strip = 0; strip < nstrip; ++strip) {
         const int xs = strip * HARRIS_STRIP, ncol = min(HARRIS_STRIP, c.sx - xs);
         const int ra = y0 + warp * rows_per, rb = y0 + c.sy;
-        /* only strips that contain image column 0 or w-1 pay for the reflected covariance columns */
-        const bool border = x0 + xs - 3 <= 0 || x0 + xs - 3 + 63 >= c.w - 1;
-        const unsigned best = border ? harris_walk<true>(job.img, c, x0, y0, xs, ncol, ra, rb, rows_per, vals, lane)
-                                     : harris_walk<false>(job.img, c, x0, y0, xs, ncol, ra, rb, rows_per, vals, lane);
+        /* rows 1 .. nfast of every warp's segment need no special case: the strip's 64 columns are inside the image,
+         * the row requested ahead (ra + 3 + i + HARRIS_AHEAD, largest for the last warp) exists, and the response row
+         * is inside the bin (only the last nw - 1 rows of the last segment can fall into the column pad) */
+        const bool cols_inside = x0 + xs - 3 >= 0 && x0 + xs - 3 + 63 <= c.w - 1;
+        const int ra_last = y0 + (nw - 1) * rows_per;
+        const int nfast = cols_inside ? max(0, min(c.h - 4 - HARRIS_AHEAD - ra_last, rows_per - nw)) : 0;
+        const unsigned best = harris_walk(job.img, c, x0, y0, xs, ncol, ra, rb, rows_per, nfast, sp, vals, lane);
         const int task = strip * nw + warp;
         if (task * 32 + lane < HARRIS_MAXIMA) mx[task * 32 + lane] = best;
     }
@@ -232,7 +282,7 @@ harris_bin_kernel(const DetectJob* __restrict__ jobs, HarrisCfg c)
             rank += (vj > vi) || (vj == vi && pj > pi);
         }
         if (rank < c.per) {
-            out[cnt - 1 - rank] = make_float2((float)(x0 + (int)pi / c.sy), (float)(y0 + (int)pi % c.sy));
+            out[cnt - 1 - rank] = make_float2((float)(x0 + (int)pi / sp), (float)(y0 + (int)pi % sp));
             if (job.resp_tmp) job.resp_tmp[(size_t)bin * c.per + cnt - 1 - rank] = __uint_as_float(vi);
         }
     }
@@ -262,9 +312,14 @@ __global__ void __launch_bounds__(128) harris_compact_kernel(const DetectJob* __
 
 } // namespace
 
+size_t viso_harris_cells(const HarrisCfg& c)
+{
+    return (size_t)c.sx * harris_col_stride(c.sy);
+}
+
 size_t viso_harris_smem(const HarrisCfg& c)
 {
-    const size_t npx = (size_t)c.sx * c.sy;
+    const size_t npx = viso_harris_cells(c);
     return ((npx + 3) & ~(size_t)3) * 4 + HARRIS_MAXIMA * 4 + ((npx * 2 + 3) & ~(size_t)3);
 }
 
