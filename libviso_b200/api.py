@@ -242,6 +242,13 @@ class Context:
                                           _p(xy), _p(rs), C.byref(n)))
         return (xy[:n.value].copy(), rs[:n.value].copy()) if with_response else xy[:n.value].copy()
 
+    # ---- MyFeatureExtractor::computeImpl, viso.cpp:1004-1024 ----
+    def extract_descriptors(self, img, kp):
+        img = np.ascontiguousarray(img, dtype=np.uint8); h, w = img.shape
+        kp = _f32(kp).reshape(-1, 2); d = np.zeros((len(kp), 121), np.float32)
+        self._ck(lib().viso_extract_descriptors(self.h, _p(img), w, h, w, _p(kp), len(kp), _p(d)))
+        return d
+
     # ---- match_circle, viso.cpp:206-243 ----
     def match_circle(self, mlr, mlrp, m11, m22):
         mlr, mlrp, m11, m22 = (_i32(a).reshape(-1, 3) for a in (mlr, mlrp, m11, m22))

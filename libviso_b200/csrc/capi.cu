@@ -987,4 +987,43 @@ int viso_detect_harris(viso_ctx* ctx, const uint8_t* img, int width, int height,
     return VISO_OK;
 }
 
+int viso_extract_descriptors(viso_ctx* ctx, const uint8_t* img, int width, int height, int pitch, const float* kp_xy, int n,
+                             float* desc)
+{
+    if (!ctx) return VISO_ERR_ARG;
+    if (n < 0 || width < 3 || height < 3 || pitch < width) return ctx->fail(VISO_ERR_ARG, "extract_descriptors: bad argument");
+    if (n == 0) return VISO_OK;
+    if (!img || !kp_xy || !desc) return ctx->fail(VISO_ERR_ARG, "extract_descriptors: null argument");
+    CK(cudaSetDevice(ctx->device));
+    struct Bufs { unsigned char* img; float2* kp; uint16_t* rows; unsigned* rsum; int *n, *flag; ExtractJob* job; } b;
+    auto carve = [&](Carver& cv) {
+        b.img = cv.take<unsigned char>((size_t)pitch * height);
+        b.kp = cv.take<float2>(n); b.rows = cv.take<uint16_t>((size_t)n * VISO_DESC_U16); b.rsum = cv.take<unsigned>(n);
+        b.n = cv.take<int>(1); b.flag = cv.take<int>(1); b.job = cv.take<ExtractJob>(1);
+    };
+    Carver measure(nullptr);
+    carve(measure);
+    int rc = ensure_scratch(ctx, measure.off);
+    if (rc) return rc;
+    Carver real(ctx->d_scr);
+    carve(real);
+    cudaStream_t s = ctx->stream;
+    const int one = 1;
+    const ExtractJob job{b.img, b.kp, b.n, b.rows, b.rsum, b.flag};
+    CK(cudaMemcpyAsync(b.img, img, (size_t)pitch * height, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.kp, kp_xy, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.n, &n, 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.flag, &one, 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.job, &job, sizeof(job), cudaMemcpyHostToDevice, s));
+    CK(viso_launch_extract(b.job, 1, n, width, height, pitch, 5, s));
+    ctx->launches += 1;
+    std::vector<uint16_t> rows((size_t)n * VISO_DESC_U16);
+    CK(cudaMemcpyAsync(rows.data(), b.rows, rows.size() * 2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    /* packed layout -> cv::Mat layout: elements are biased by 1024, 121 of the 128 are used */
+    for (int k = 0; k < n; ++k)
+        for (int c = 0; c < 121; ++c) desc[(size_t)k * 121 + c] = (float)((int)rows[(size_t)k * VISO_DESC_U16 + c] - 1024);
+    return VISO_OK;
+}
+
 } /* extern "C" */

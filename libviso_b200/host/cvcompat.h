@@ -1,6 +1,6 @@
 /*
  * cvcompat.h -- the few OpenCV core types the libviso hot-path API is written in (cv::Mat of CV_64F / CV_32F /
- * CV_32S, KeyPoint, Point2f, Vec3i / Vec4i), for builds where OpenCV itself is not installed (this image has no
+ * CV_32S / CV_8U, KeyPoint, Point2f, Vec3i / Vec4i), for builds where OpenCV itself is not installed (this image has no
  * OpenCV C++ headers: SURVEY.md 8c).  When <opencv2/core/core.hpp> exists it is used instead and this file adds
  * nothing.  Only what libviso_b200/host/ and its tests touch is provided; layouts follow OpenCV (row-major,
  * ref-counted buffer, at<T>(r,c), ptr<T>(r)).
@@ -25,6 +25,7 @@
 #include <memory>
 #include <vector>
 
+#define CV_8U 0
 #define CV_32S 4
 #define CV_32F 5
 #define CV_64F 6
@@ -32,6 +33,7 @@
 namespace cv {
 
 template <class T> struct DataType;
+template <> struct DataType<unsigned char> { enum { type = CV_8U }; };
 template <> struct DataType<int> { enum { type = CV_32S }; };
 template <> struct DataType<float> { enum { type = CV_32F }; };
 template <> struct DataType<double> { enum { type = CV_64F }; };
@@ -75,7 +77,7 @@ public:
 
     void create(int r, int c, int type)
     {
-        assert(type == CV_32S || type == CV_32F || type == CV_64F);
+        assert(type == CV_8U || type == CV_32S || type == CV_32F || type == CV_64F);
         rows = r; cols = c; type_ = type;
         const size_t bytes = (size_t)r * c * elemSize();
         buf_ = std::shared_ptr<unsigned char>(new unsigned char[bytes ? bytes : 1], std::default_delete<unsigned char[]>());
@@ -91,7 +93,7 @@ public:
     int type() const { return type_; }
     bool empty() const { return rows == 0 || cols == 0; }
     bool isContinuous() const { return true; }
-    size_t elemSize() const { return type_ == CV_64F ? 8 : 4; }
+    size_t elemSize() const { return type_ == CV_64F ? 8 : type_ == CV_8U ? 1 : 4; }
     size_t total() const { return (size_t)rows * cols; }
     template <class T> T& at(int r, int c) { assert(DataType<T>::type == type_); return reinterpret_cast<T*>(data)[(size_t)r * cols + c]; }
     template <class T> const T& at(int r, int c) const { assert(DataType<T>::type == type_); return reinterpret_cast<const T*>(data)[(size_t)r * cols + c]; }
@@ -109,6 +111,7 @@ public:
         for (size_t i = 0; i < total(); ++i) {
             if (type_ == CV_64F) reinterpret_cast<double*>(data)[i] = v;
             else if (type_ == CV_32F) reinterpret_cast<float*>(data)[i] = (float)v;
+            else if (type_ == CV_8U) data[i] = (unsigned char)v;
             else reinterpret_cast<int*>(data)[i] = (int)v;
         }
     }
@@ -118,6 +121,7 @@ private:
     {
         if (type_ == CV_64F) at<double>(r, c) = v;
         else if (type_ == CV_32F) at<float>(r, c) = (float)v;
+        else if (type_ == CV_8U) at<unsigned char>(r, c) = (unsigned char)v;
         else at<int>(r, c) = (int)v;
     }
     int type_ = -1;

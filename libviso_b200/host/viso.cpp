@@ -348,3 +348,115 @@ vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, FeatureSequence& fra
     viso_seq_destroy(seq);
     return poses;
 }
+
+/* ---- front end: detector, extractor, images -> poses ---- */
+
+namespace {
+int g_max_features = 1200;   /* viso.cpp:1172 */
+
+const unsigned char* image8(const Mat& image)
+{
+    if (image.empty() || image.type() != cv::DataType<unsigned char>::type || !image.isContinuous())
+        throw viso_b200_error(VISO_ERR_ARG, "expected a continuous 8-bit single-channel image");
+    return image.ptr<unsigned char>(0);
+}
+} // namespace
+
+namespace viso_b200 {
+void set_max_features(int n)
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    g_max_features = n;
+}
+} // namespace viso_b200
+
+HarrisBinnedFeatureDetector::HarrisBinnedFeatureDetector(int radius, int n, int nbinx, int nbiny, float k, int block_size,
+                                                         int aperture_size)
+    : m_radius(radius), m_nbinx(nbinx), m_nbiny(nbiny), m_n(n), m_k(k)
+{
+    assert(nbinx > 0 && nbiny > 0);   /* viso.cpp:919 */
+    if (block_size != 3 || aperture_size != 5)
+        throw viso_b200_error(VISO_ERR_DOMAIN, "HarrisBinnedFeatureDetector: only block_size 3, aperture_size 5 (the reference's defaults)");
+}
+
+void HarrisBinnedFeatureDetector::detect(const Mat& image, KeyPoints& kp) const
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    const unsigned char* img = image8(image);
+    vector<float> xy((size_t)std::max(m_n, 1) * 2), resp(std::max(m_n, 1));
+    int32_t n = 0;
+    ck(viso_detect_harris(ctx(), img, image.cols, image.rows, image.cols, m_n, m_nbinx, m_nbiny, m_k, xy.data(), resp.data(), &n));
+    kp.clear();
+    kp.reserve(n);
+    for (int i = 0; i < n; ++i) {
+        KeyPoint k(xy[2 * i], xy[2 * i + 1], (float)(2 * m_radius + 1));   /* viso.cpp:967-969 */
+        k.response = resp[i];
+        kp.push_back(k);
+    }
+}
+
+MyFeatureExtractor::MyFeatureExtractor(int descriptor_radius) : m_descriptor_radius(descriptor_radius)
+{
+    if (descriptor_radius != 5) throw viso_b200_error(VISO_ERR_DOMAIN, "MyFeatureExtractor: only descriptor radius 5 (viso.cpp:1174)");
+}
+
+void MyFeatureExtractor::compute(const Mat& image, KeyPoints& kp, Mat& d) const
+{
+    std::lock_guard<std::mutex> l(G().mu);
+    const unsigned char* img = image8(image);
+    d = Mat((int)kp.size(), descriptorSize(), cv::DataType<float>::type, 0.0);   /* viso.cpp:1008 */
+    if (kp.empty()) return;
+    const vector<float> a = kp_array(kp);
+    ck(viso_extract_descriptors(ctx(), img, image.cols, image.rows, image.cols, a.data(), (int)kp.size(), d.ptr<float>(0)));
+}
+
+vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, StereoImageSource& images)
+{
+    vector<Mat> poses;
+    poses.push_back(Mat::eye(4, 4, cv::DataType<double>::type)); /* viso.cpp:1189-1190 */
+    vector<image_pair> pairs;
+    image_pair ip;
+    while (images.next(ip)) {                                    /* viso.cpp:1205 */
+        if (ip.first.rows != ip.second.rows || ip.first.cols != ip.second.cols ||
+            (!pairs.empty() && (ip.first.rows != pairs[0].first.rows || ip.first.cols != pairs[0].first.cols)))
+            throw viso_b200_error(VISO_ERR_ARG, "sequence_odometry: all images of a sequence must have one size");
+        image8(ip.first); image8(ip.second);
+        pairs.push_back(image_pair(ip.first.clone(), ip.second.clone()));
+    }
+    std::lock_guard<std::mutex> l(G().mu);
+    Global& g = G();
+    const int F = (int)pairs.size();
+    if (F == 0) return poses;
+    struct param prm;
+    prm.base = 0; prm.calib.f = 0; prm.calib.cu = 0; prm.calib.cv = 0;
+    viso_seq* seq = nullptr;
+    ck(viso_seq_create(ctx(), F, std::max(g_max_features, 1), 121, prm.ransac_iter, &seq));
+    try {
+        ck(viso_seq_set_calib(seq, p1.ptr<double>(0), p2.ptr<double>(0)));
+        ck(viso_seq_set_image_size(seq, pairs[0].first.cols, pairs[0].first.rows));
+        ck(viso_seq_set_detector(seq, g_max_features, 24, 5, .04f));   /* detector(5, MAX_FEATURE_NUM), viso.cpp:1173 */
+        for (int t = 0; t < F; ++t) ck(viso_seq_upload_frame_raw(seq, t, pairs[t].first.ptr<unsigned char>(0), pairs[t].second.ptr<unsigned char>(0)));
+        ck(viso_sync(ctx()));
+        vector<uint32_t> seeds((size_t)F * prm.ransac_iter * 3);
+        {
+            std::mt19937 gen(g.seed);
+            for (auto& s : seeds) s = (uint32_t)gen();
+        }
+        viso_param p = to_c(prm);
+        ck(viso_seq_run(seq, &p, seeds.data()));
+        vector<viso_record> rec(F);
+        ck(viso_seq_download(seq, rec.data()));
+        vector<double> chained((size_t)F * 16);
+        const int np = viso_chain_poses(rec.data(), F, chained.data()); /* viso.cpp:1313-1321 */
+        for (int i = 1; i < np; ++i) {
+            Mat pose(4, 4, cv::DataType<double>::type);
+            std::memcpy(pose.ptr<double>(0), &chained[(size_t)16 * i], 16 * sizeof(double));
+            poses.push_back(pose);
+        }
+    } catch (...) {
+        viso_seq_destroy(seq);
+        throw;
+    }
+    viso_seq_destroy(seq);
+    return poses;
+}

@@ -18,6 +18,11 @@
  *   tr2mat                             viso.h:162          identical signature
  *   F_from_P<double>                   mvg.h:41-66         F_from_P(P1, P2)
  *   per-frame loop of sequence_odometry viso.cpp:1205-1327 sequence_odometry(P1, P2, FeatureSequence&)
+ *   HarrisBinnedFeatureDetector        viso.cpp:911-979    same constructor, detect(image, kp)
+ *   MyFeatureExtractor                 viso.cpp:981-1025   same constructor, compute(image, kp, d)
+ *   sequence_odometry                  viso.h:138-139      sequence_odometry(P1, P2, StereoImageSource&): images in,
+ *                                                          poses out; StereoImageGenerator's cv::imread (viso.h:81-101)
+ *                                                          is replaced by any source of 8-bit image pairs
  *
  * RANSAC sampling: the reference seeds a fresh std::mt19937 from std::random_device per hypothesis
  * (viso.cpp:93-95), which is not reproducible.  Here the triples come from one std::mt19937 stream through the
@@ -130,8 +135,51 @@ void tr2mat(vector<double> tr, Mat& Tr);
 
 Mat F_from_P(const Mat& P1, const Mat& P2);
 
-/* One frame's front-end output (HarrisBinnedFeatureDetector + MyFeatureExtractor, viso.cpp:1226-1231 -- the
- * front-end itself is outside this library's scope). */
+/* reference src/viso.cpp:911-979.  detect() clears nothing (cv::FeatureDetector::detect does: kp is replaced). The
+ * reference leaves m_k uninitialised (:915-919, :978); here the constructor argument is stored.  Keypoint order
+ * inside a bin: ascending (|response|, x, y) (include/viso_b200.h, viso_detect_harris). */
+class HarrisBinnedFeatureDetector {
+public:
+    HarrisBinnedFeatureDetector(int radius, int n, int nbinx = 24, int nbiny = 5, float k = .04f, int block_size = 3,
+                                int aperture_size = 5);
+    void detect(const Mat& image /* CV_8U */, KeyPoints& kp) const;
+
+private:
+    int m_radius, m_nbinx, m_nbiny, m_n;
+    float m_k;
+};
+
+/* reference src/viso.cpp:981-1025: d = kp.size() x (2r+1)^2 CV_32F; only r = 5 (the pipeline's, viso.cpp:1174) */
+class MyFeatureExtractor {
+public:
+    explicit MyFeatureExtractor(int descriptor_radius);
+    int descriptorSize() const { return (2 * m_descriptor_radius + 1) * (2 * m_descriptor_radius + 1); }
+    void compute(const Mat& image /* CV_8U */, KeyPoints& kp, Mat& d) const;
+
+private:
+    int m_descriptor_radius;
+};
+
+typedef pair<Mat, Mat> image_pair;   /* reference src/viso.h: left, right (CV_8U, same size) */
+
+/* Source of stereo pairs: the analogue of StereoImageGenerator::operator() (viso.h:86-96) without cv::imread;
+ * next() returns false when the sequence ends (the reference stops at the first unreadable pair). */
+class StereoImageSource {
+public:
+    virtual ~StereoImageSource() {}
+    virtual bool next(image_pair& out) = 0;
+};
+
+namespace viso_b200 {
+void set_max_features(int n);   /* MAX_FEATURE_NUM of sequence_odometry; the reference hard-codes 1200 (viso.cpp:1172) */
+}
+
+/* sequence_odometry (viso.h:138-139, viso.cpp:1167-1330) from images: Harris detection, descriptors, matching, circle
+ * closure, triangulation and RANSAC/Gauss-Newton all on the device; only the images go up and 64 bytes per frame
+ * pair come back.  Debug image dumps (dbg_dir) are not produced. */
+vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, StereoImageSource& images);
+
+/* One frame's front-end output (HarrisBinnedFeatureDetector + MyFeatureExtractor, viso.cpp:1226-1231). */
 struct FrameFeatures {
     KeyPoints kp1, kp2;   /* left, right */
     Descriptors d1, d2;   /* n x 121 CV_32F */

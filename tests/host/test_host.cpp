@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 
 static int g_checks = 0;
@@ -333,8 +334,131 @@ static void test_mvg_estimation()
     REQUIRE(std::fabs(Xr.at<float>(2, 0) - 1) < 1e-3);
 }
 
+
+// ---- front end: HarrisBinnedFeatureDetector, MyFeatureExtractor and the image-driven sequence_odometry
+// (viso.cpp:911-1025, :1167-1330) against the oracle.  Images: a band-limited random texture seen at a constant
+// disparity (8 px), shifted 3 px per frame.
+struct ShiftedTexture : StereoImageSource {
+    int W = 1241, H = 376, n = 4, t = 0;
+    vector<unsigned char> tex;   // H x (W + 64)
+    ShiftedTexture()
+    {
+        const int TW = W + 64;
+        std::mt19937 gen(21);
+        std::uniform_int_distribution<> u(0, 255);
+        vector<float> a((size_t)H * TW), b((size_t)H * TW);
+        for (auto& v : a) v = (float)u(gen);
+        for (int pass = 0; pass < 2; ++pass) {   // two 3 x 3 box blurs
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < TW; ++x) {
+                    float sum = 0; int cnt = 0;
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int yy = y + dy, xx = x + dx;
+                            if (yy < 0 || yy >= H || xx < 0 || xx >= TW) continue;
+                            sum += a[(size_t)yy * TW + xx]; ++cnt;
+                        }
+                    b[(size_t)y * TW + x] = sum / cnt;
+                }
+            a.swap(b);
+        }
+        tex.resize(a.size());
+        for (size_t i = 0; i < a.size(); ++i) tex[i] = (unsigned char)std::min(255.f, std::max(0.f, (a[i] - 127.5f) * 4.f + 127.5f));
+    }
+    Mat view(int x0) const
+    {
+        Mat m(H, W, CV_8U);
+        for (int y = 0; y < H; ++y) std::memcpy(m.ptr<unsigned char>(y), &tex[(size_t)y * (W + 64) + x0], W);
+        return m;
+    }
+    image_pair pair_at(int i) const { return image_pair(view(20 + 3 * i), view(28 + 3 * i)); }
+    bool next(image_pair& out) override
+    {
+        if (t >= n) return false;
+        out = pair_at(t++);
+        return true;
+    }
+};
+
+static void test_front_end()
+{
+    Mat P1 = Mat::zeros(3, 4, CV_64F), P2;
+    P1.at<double>(0, 0) = 718.856; P1.at<double>(0, 2) = 607.1928;
+    P1.at<double>(1, 1) = 718.856; P1.at<double>(1, 2) = 185.2157;
+    P1.at<double>(2, 2) = 1;
+    P2 = P1.clone();
+    P2.at<double>(0, 3) = -386.1448;
+    ShiftedTexture src;
+    const int W = src.W, H = src.H, NF = 1200;   // MAX_FEATURE_NUM, viso.cpp:1172
+
+    // detector + extractor, one image (viso.cpp:1226-1231)
+    HarrisBinnedFeatureDetector detector(5, NF);
+    MyFeatureExtractor extractor(5);
+    const image_pair p0 = src.pair_at(0);
+    KeyPoints kp;
+    detector.detect(p0.first, kp);
+    vector<float> okp((size_t)NF * 2), oresp(NF);
+    const int on = vo_detect_harris_binned(p0.first.ptr<unsigned char>(0), H, W, NF, 24, 5, .04f, 1, okp.data(), oresp.data());
+    REQUIRE(on == NF && (int)kp.size() == on);
+    for (int i = 0; i < on; ++i) {
+        REQUIRE(kp[i].pt.x == okp[2 * i] && kp[i].pt.y == okp[2 * i + 1] && kp[i].response == oresp[i]);
+        REQUIRE(kp[i].size == 11.f);
+    }
+    Mat d;
+    extractor.compute(p0.first, kp, d);
+    REQUIRE(d.rows == on && d.cols == 121 && extractor.descriptorSize() == 121);
+    vector<float> sob((size_t)W * H), od((size_t)on * 121);
+    vo_sobel_x(p0.first.ptr<unsigned char>(0), H, W, sob.data());
+    vo_extract_descriptors(sob.data(), H, W, okp.data(), on, 5, od.data());
+    REQUIRE(std::memcmp(d.ptr<float>(0), od.data(), od.size() * 4) == 0);
+
+    // images -> poses in one submission vs the oracle's front end + sequential loop, same seeds
+    viso_b200::set_ransac_seed(7);
+    vector<Mat> poses = sequence_odometry(P1, P2, src);
+    const int nF = src.n, Hy = 50;
+    vector<int32_t> nL(nF), nR(nF);
+    vector<int64_t> offL(nF), offR(nF);
+    vector<float> kpL, kpR, dL, dR;
+    for (int t = 0; t < nF; ++t) {
+        const image_pair ip = src.pair_at(t);
+        for (int side = 0; side < 2; ++side) {
+            const Mat& im = side ? ip.second : ip.first;
+            vector<float> k2((size_t)NF * 2);
+            const int n = vo_detect_harris_binned(im.ptr<unsigned char>(0), H, W, NF, 24, 5, .04f, 1, k2.data(), nullptr);
+            vector<float> dd((size_t)n * 121);
+            vo_sobel_x(im.ptr<unsigned char>(0), H, W, sob.data());
+            vo_extract_descriptors(sob.data(), H, W, k2.data(), n, 5, dd.data());
+            vector<float>& K = side ? kpR : kpL; vector<float>& D = side ? dR : dL;
+            (side ? nR : nL)[t] = n; (side ? offR : offL)[t] = (int64_t)K.size() / 2;
+            K.insert(K.end(), k2.begin(), k2.begin() + 2 * n); D.insert(D.end(), dd.begin(), dd.end());
+        }
+    }
+    vector<uint32_t> seeds((size_t)nF * Hy * 3);
+    {
+        std::mt19937 gen(7);
+        for (auto& s : seeds) s = (uint32_t)gen();
+    }
+    vo_param vp;
+    vo_param_default(&vp);
+    vp.ransac_iter = Hy;
+    vector<vo_record> rec(nF);
+    vector<double> oposes((size_t)(nF + 1) * 16);
+    int32_t onp = 0;
+    REQUIRE(vo_sequence(nF, nL.data(), nR.data(), offL.data(), offR.data(), kpL.data(), kpR.data(), dL.data(), dR.data(),
+                        121, P1.ptr<double>(0), P2.ptr<double>(0), &vp, seeds.data(), rec.data(), nullptr, nullptr,
+                        nullptr, nullptr, nullptr, nullptr, oposes.data(), &onp) == 0);
+    REQUIRE((int)poses.size() == onp);
+    for (int i = 0; i < onp; ++i)
+        for (int k = 0; k < 16; ++k) REQUIRE(std::fabs(poses[i].ptr<double>(0)[k] - oposes[(size_t)16 * i + k]) < 1e-6);
+    int okc = 0;
+    for (int t = 1; t < nF; ++t) okc += rec[t].ok;
+    std::printf("front end: %d keypoints/image, %d poses, %d of %d frame pairs ok, n_circ %d\n", on, onp, okc, nF - 1, rec[1].n_circ);
+    REQUIRE(onp >= 2 && rec[1].n_circ > 100);
+}
+
 int main()
 {
+    test_front_end();
     test_mvg_estimation();
     test_nl_rigid_motion1();
     test_frame_loop();

@@ -665,3 +665,19 @@ def test_sequence_from_raw_images(ctx, api, oracle, small_sequence):
     seq.run(pg)
     assert seq.download().tobytes() == rec.tobytes()
     seq.close()
+
+
+@pytest.mark.gpu
+def test_extract_descriptors_standalone(ctx, oracle, small_sequence):
+    """viso_extract_descriptors (MyFeatureExtractor::computeImpl, viso.cpp:1004-1024) in the cv::Mat layout: interior,
+    border (the > 0 rule at :1018), half-integer coordinates (Point2i rounds half to even)"""
+    frames, _ = small_sequence
+    img = frames[0]["imL"]
+    h, w = img.shape
+    rng = np.random.default_rng(9)
+    kp = np.concatenate([frames[0]["kpL"][:200],
+                         np.array([[0, 0], [w - 1, h - 1], [3, 2], [w - 2, 5], [5, h - 3], [0.5, 1.5], [2.5, 3.5], [10.5, 7.5]], np.float32),
+                         np.stack([rng.integers(0, w, 100), rng.integers(0, h, 100)], 1).astype(np.float32)])
+    want = oracle.extract_descriptors(oracle.sobel_x(img), kp)
+    got = ctx.extract_descriptors(img, kp)
+    assert got.tobytes() == want.tobytes()
