@@ -681,3 +681,36 @@ def test_extract_descriptors_standalone(ctx, oracle, small_sequence):
     want = oracle.extract_descriptors(oracle.sobel_x(img), kp)
     got = ctx.extract_descriptors(img, kp)
     assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.gpu
+def test_raw_sequence_with_featureless_frames(ctx, api, oracle, small_sequence):
+    """a flat image pair in the middle of a sequence: the detector finds nothing there (every response is 0,
+    viso.cpp:956), the two frame pairs around it yield no pose (< 3 circular matches, viso.cpp:1283-1288), the others
+    are unaffected; and a pair whose right image is flat (stereo matching finds nothing)"""
+    from libviso_b200 import synth
+    frames, _ = small_sequence
+    P1, P2 = synth.kitti_calib()
+    H, nfeat = 50, 360
+    flat = np.full((synth.H, synth.W), 77, np.uint8)
+    imgs = [(frames[0]["imL"], frames[0]["imR"]), (frames[1]["imL"], frames[1]["imR"]), (flat, flat),
+            (frames[3]["imL"], frames[3]["imR"]), (frames[4]["imL"], flat), (frames[5]["imL"], frames[5]["imR"])]
+    seeds = make_seeds(len(imgs), H)
+    oframes = oracle.frames_from_images(imgs, nfeat)
+    assert len(oframes[2]["kpL"]) == 0 and len(oframes[4]["kpR"]) == 0
+    o = oracle.sequence(oframes, P1, P2, oracle.param_default(ransac_iter=H), seeds)
+    seq = ctx.sequence(len(imgs), nfeat, 121, H)
+    seq.set_calib(P1, P2)
+    seq.set_image_size(synth.W, synth.H)
+    seq.set_detector(nfeat)
+    for t, (a, b) in enumerate(imgs):
+        seq.upload_frame_raw_images(t, a, b)
+    seq.run(api.param_default(ransac_iter=H), seeds)
+    rec = seq.download()
+    for t, f in enumerate(oframes):
+        assert np.array_equal(seq.get_keypoints(t, 0), f["kpL"]) and np.array_equal(seq.get_keypoints(t, 1), f["kpR"]), t
+    for k in ("ok", "n_inliers", "n_circ", "best_hyp"):
+        assert np.array_equal(rec[k], o["records"][k]), k
+    assert_tr_close(rec["tr"], o["records"]["tr"])
+    assert rec["ok"].tolist() == [0, 1, 0, 0, 0, 0]
+    seq.close()
