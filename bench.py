@@ -236,6 +236,29 @@ class StdoutGuard:
         os.dup2(2, 1)
 
 
+def bind_to_gpu_cpus(local_rank):
+    """The pinned host buffers are first-touched by this process: keep it on the CPUs (NUMA node) next to its GPU.
+    A no-op where NVML reports every CPU (single-socket boxes)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].strip().isdigit():
+                idx = int(ids[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception as e:  # no NVML, restricted cpuset, ...: keep the inherited affinity
+        print(f"[bench] CPU binding skipped: {e}", file=sys.stderr)
+
+
 def main():
     args = parse_args()
     guard = StdoutGuard()
@@ -253,6 +276,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libviso_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_cpus(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's own log lines: keep stdout to the one JSON line

@@ -140,6 +140,15 @@ def test_match_desc_epipolar_gate_general_F(ctx, api, oracle):
     o = oracle.match_desc(kp1, kp2, d1, d2, so)
     assert o["valid"].sum() > 100
     dense_equal(ctx.match_desc_dense(kp1, kp2, d1, d2, sg), o)
+    # the mono configuration of calibratedSFM (viso.cpp:1384-1390): general F, ratio test .9, radius 10
+    so, sg = oracle.match_params_stereo(F), api.match_params_stereo(F)
+    for s_ in (so, sg):
+        s_.sampson_thresh = 4.0; s_.enforce_2nd_best = 1; s_.ratio_2nd_best = .9; s_.radius = 10.0
+    kp2b = kp1 + rng.integers(-3, 4, size=kp1.shape).astype(np.float32)     # targets near the queries
+    d2b = np.clip(d1 + rng.integers(-40, 41, size=d1.shape), -1020, 1020).astype(np.float32)
+    o = oracle.match_desc(kp1, kp2b, d1, d2b, so)
+    dense_equal(ctx.match_desc_dense(kp1, kp2b, d1, d2b, sg), o)
+    assert np.array_equal(ctx.match_desc(kp1, kp2b, d1, d2b, sg), o["matches"])
     # degenerate F: every Sampson distance is NaN -> nothing matches
     so, sg = oracle.match_params_stereo(np.zeros((3, 3))), api.match_params_stereo(np.zeros((3, 3)))
     o = oracle.match_desc(kp1, kp2, d1, d2, so)
