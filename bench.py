@@ -46,15 +46,21 @@ def parse_args():
                     help="distinct rendered frames; the sequence drives back and forth over them (every frame has "
                          "its own HBM copy, so the working set is the full --frames)")
     ap.add_argument("--cpu-pairs", type=int, default=96, help="frame pairs in the cpu_baseline sample")
-    ap.add_argument("--chunk", type=int, default=125, help="frames per upload/compute chunk of the e2e pipeline")
+    ap.add_argument("--chunk", type=int, default=0,
+                    help="frames per upload/compute chunk of the e2e pipeline (0: 125, or 250 with --input raw -- measured)")
     ap.add_argument("--e2e-buffers", type=int, default=2, choices=[1, 2],
                     help="sequence objects (each on its own context / streams) taking alternate e2e steps")
     ap.add_argument("--input", default="images", choices=["images", "descriptors", "raw"],
                     help="what crosses the boundary per frame: the two 8-bit images + keypoints (descriptors extracted "
                          "on the device, viso.cpp:1004-1024) or the reference's n x 121 f32 descriptor matrices")
+    ap.add_argument("--e2e-separate-copy-streams", action="store_true",
+                    help="A/B switch: every e2e lane uploads on its own copy stream (pieces of the two lanes interleave)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.chunk <= 0:
+        args.chunk = 250 if args.input == "raw" else 125
+    return args
 
 
 def pingpong(n_frames, n_unique):
@@ -390,6 +396,8 @@ def main():
         if args.e2e_buffers > 1:
             ctx2 = api.Context(local_rank)
             ctx2.set_image_extent(synth.W, synth.H)
+            if not args.e2e_separate_copy_streams:
+                ctx2.share_copy_stream(ctx)   # uploads of the two lanes are served FIFO, not interleaved
             seq2 = ctx2.sequence(F, cap, 121, H)
             seq2.set_calib(P1, P2)
             if use_img:

@@ -82,6 +82,11 @@ void viso_destroy(viso_ctx* ctx);
 const char* viso_last_error(const viso_ctx* ctx);
 void* viso_stream(viso_ctx* ctx);                  /* the cudaStream_t every kernel of this context is launched on */
 int viso_sync(viso_ctx* ctx);
+/* Uploads of a context's sequence objects run on the context's own copy stream.  Several contexts that take turns on
+ * one PCIe link (double buffering) should share ONE copy stream so that their uploads are served first-in first-out
+ * instead of interleaved piece by piece: `ctx` uses `owner`'s copy stream from now on (owner == NULL: its own again).
+ * `owner` must outlive `ctx`'s use of it. */
+int viso_share_copy_stream(viso_ctx* ctx, viso_ctx* owner);
 /* extent of the uniform candidate grid (pixels); coordinates outside are clamped into border cells, so any
  * value is correct, a matching one is fast.  Default 1248 x 384. */
 int viso_set_image_extent(viso_ctx* ctx, int width, int height);

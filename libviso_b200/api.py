@@ -176,6 +176,10 @@ class Context:
         if rc != 0:
             raise VisoError(rc, lib().viso_last_error(self.h).decode())
 
+    def share_copy_stream(self, owner):
+        """uploads of this context's sequences are queued behind `owner`'s (first-in first-out over one PCIe link)"""
+        self._ck(lib().viso_share_copy_stream(self.h, owner.h if owner is not None else None))
+
     def sync(self):
         self._ck(lib().viso_sync(self.h))
 

@@ -174,7 +174,18 @@ int viso_create(viso_ctx** out, int device)
         delete ctx;
         return VISO_ERR_CUDA;
     }
+    ctx->own_copy_stream = ctx->copy_stream;
     *out = ctx;
+    return VISO_OK;
+}
+
+int viso_share_copy_stream(viso_ctx* ctx, viso_ctx* owner)
+{
+    if (!ctx) return VISO_ERR_ARG;
+    if (owner && owner->device != ctx->device) return ctx->fail(VISO_ERR_ARG, "share_copy_stream: contexts on different devices");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copy_stream = owner ? owner->own_copy_stream : ctx->own_copy_stream;
     return VISO_OK;
 }
 
@@ -187,7 +198,8 @@ void viso_destroy(viso_ctx* ctx)
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     cudaStreamSynchronize(ctx->copy_stream);
-    cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->own_copy_stream);
+    cudaStreamDestroy(ctx->own_copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

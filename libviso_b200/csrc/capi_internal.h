@@ -22,6 +22,7 @@ struct viso_ctx {
     size_t d_cap = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaStream_t copy_stream = nullptr;   /* host -> device uploads of sequence objects (overlap with compute) */
+    cudaStream_t own_copy_stream = nullptr; /* the one this context created (copy_stream may be another context's) */
 
     int fail(int code, const std::string& msg)
     {

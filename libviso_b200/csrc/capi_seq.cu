@@ -473,14 +473,23 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
     if (s->H_cur != param->ransac_iter) return ctx->fail(VISO_ERR_ARG, "seq_run: seeds were set for a different ransac_iter");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    /* everything uploaded so far (frames, seeds) is visible to the kernels below */
+    const int nf = t1 - t0;
+    /* The per-frame counts and flags go up on the COPY stream, behind the frames they describe: a host-to-device
+     * copy on the compute stream would queue on the copy engine behind every upload already enqueued by other
+     * sequence objects (measured: it serialises double-buffered pipelines completely).  Kernels of an earlier
+     * submission may still read these words, hence the guard. */
+    {
+        int rc = upload_guard(s, t0);
+        if (rc) return rc;
+        cudaStream_t cs = ctx->copy_stream;
+        CK(cudaMemcpyAsync(s->nL + t0, s->h_nL + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(s->nR + t0, s->h_nR + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(s->from_image + t0, s->h_from_image + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, cs));
+        if (s->det_set) CK(cudaMemcpyAsync(s->detect + t0, s->h_detect + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, cs));
+    }
+    /* everything uploaded so far (frames, seeds, counts) is visible to the kernels below */
     CK(cudaEventRecord(s->ev_copy, ctx->copy_stream));
     CK(cudaStreamWaitEvent(st, s->ev_copy, 0));
-    const int nf = t1 - t0;
-    CK(cudaMemcpyAsync(s->nL + t0, s->h_nL + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->nR + t0, s->h_nR + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->from_image + t0, s->h_from_image + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
-    if (s->det_set) CK(cudaMemcpyAsync(s->detect + t0, s->h_detect + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
     if (t0 == 0) {
         CK(cudaMemsetAsync(s->pairs, 0, 16, st));
         CK(cudaMemsetAsync(s->err, 0, 4, st));
