@@ -491,8 +491,8 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
     CK(cudaEventRecord(s->ev_copy, ctx->copy_stream));
     CK(cudaStreamWaitEvent(st, s->ev_copy, 0));
     if (t0 == 0) {
-        CK(cudaMemsetAsync(s->pairs, 0, 16, st));
-        CK(cudaMemsetAsync(s->err, 0, 4, st));
+        CK(viso_launch_zero(s->pairs, 4, st));
+        CK(viso_launch_zero(s->err, 1, st));
     }
     int max_n = 0, max_nL = 0, any_img = 0, any_f32 = 0, any_det = 0;
     for (int t = t0; t < t1; ++t) {

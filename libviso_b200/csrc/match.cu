@@ -914,6 +914,17 @@ cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dle
     return cudaGetLastError();
 }
 
+__global__ void zero_words_kernel(int* p, int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0;
+}
+
+cudaError_t viso_launch_zero(void* p, int n_words, cudaStream_t s)
+{
+    zero_words_kernel<<<1, 32, 0, s>>>(static_cast<int*>(p), n_words);
+    return cudaGetLastError();
+}
+
 cudaError_t viso_launch_extract(const ExtractJob* jobs, int n_jobs, int max_n, int width, int height, int pitch, int radius,
                                 cudaStream_t s)
 {
@@ -976,7 +987,9 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
         if (e != cudaSuccess) return e;
         attr_set = 1;
     }
-    cudaError_t e = cudaMemsetAsync(n_pending, 0, sizeof(int), s);
+    /* a kernel, not cudaMemsetAsync: memsets and copies on the compute stream can be scheduled on a copy engine and
+     * then wait behind every upload queued there (see viso_seq_run_range) */
+    cudaError_t e = viso_launch_zero(n_pending, 1, s);
     if (e != cudaSuccess) return e;
     const int tiles = ((g.gx + VISO_TILE_W - 1) / VISO_TILE_W) * ((g.gy + VISO_TILE_H - 1) / VISO_TILE_H);
     sad_match_kernel<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, ql_cap, sad_pairs, n_pending);

@@ -181,6 +181,7 @@ cudaError_t viso_launch_extract(const ExtractJob* jobs, int n_jobs, int max_n, i
 size_t viso_harris_smem(const HarrisCfg& c);
 size_t viso_harris_cells(const HarrisCfg& c);   /* response slots a bin occupies in shared memory */
 cudaError_t viso_launch_detect(const DetectJob* jobs, int n_jobs, const HarrisCfg& c, cudaStream_t s);
+cudaError_t viso_launch_zero(void* p, int n_words, cudaStream_t s);   /* a few words, by a kernel */
 cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStream_t s);
 cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
                               GridCfg g, unsigned long long* sad_pairs, int* n_pending, cudaStream_t s, int* launches);
