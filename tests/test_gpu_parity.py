@@ -723,3 +723,59 @@ def test_raw_sequence_with_featureless_frames(ctx, api, oracle, small_sequence):
     assert_tr_close(rec["tr"], o["records"]["tr"])
     assert rec["ok"].tolist() == [0, 1, 0, 0, 0, 0]
     seq.close()
+
+
+@pytest.mark.gpu
+def test_detect_harris_random_geometries(ctx, oracle):
+    """40 random image sizes / bin layouts / quotas (tiny bins, one-row bins, bins wider than one 58-column strip,
+    widths below the 64-column strip, bins reaching the last row and column) against the oracle, bit for bit"""
+    rng = np.random.default_rng(77)
+    for case in range(40):
+        h, w = int(rng.integers(8, 160)), int(rng.integers(8, 260))
+        nbx, nby = int(rng.integers(1, min(7, w) + 1)), int(rng.integers(1, min(7, h) + 1))
+        per = int(rng.integers(1, 40))
+        n = nbx * nby * per + int(rng.integers(0, nbx * nby))
+        kind = case % 4
+        if kind == 0:
+            img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+        elif kind == 1:   # smooth: blurred noise, like the synthetic frames
+            a = rng.random((h + 4, w + 4))
+            a = sum(a[i:i + h, j:j + w] for i in range(5) for j in range(5)) / 25
+            img = np.clip((a - 0.5) * 900 + 128, 0, 255).astype(np.uint8)
+        elif kind == 2:   # piecewise constant: most responses are exactly 0
+            img = np.repeat(np.repeat(rng.integers(0, 256, size=((h + 15) // 16, (w + 15) // 16), dtype=np.uint8), 16, 0), 16, 1)[:h, :w]
+            img = np.ascontiguousarray(img)
+        else:             # two grey levels: many exactly equal responses (ties at the cut)
+            img = ((rng.random((h, w)) < 0.08) * 200 + 20).astype(np.uint8)
+        want, wresp = oracle.detect_harris_binned(img, n, nbx, nby, 0.04, order_rule=1, with_response=True)
+        got, gresp = ctx.detect_harris(img, n, nbx, nby, 0.04, with_response=True)
+        assert np.array_equal(got, want), (case, h, w, nbx, nby, n)
+        assert gresp.tobytes() == wresp.tobytes(), (case, h, w, nbx, nby, n)
+
+
+@pytest.mark.gpu
+def test_detector_argument_errors(ctx, api):
+    seq = ctx.sequence(2, 600, 121, 10)
+    img = np.zeros((64, 96), np.uint8)
+    with pytest.raises(api.VisoError):          # image size first
+        seq.set_detector(240)
+    seq.set_image_size(96, 64)
+    with pytest.raises(api.VisoError):          # raw upload needs a detector
+        seq.upload_frame_raw_images(0, img, img)
+    with pytest.raises(api.VisoError):          # more keypoints than the sequence object can hold
+        seq.set_detector(24 * 5 * 6)
+    with pytest.raises(api.VisoError):          # fewer features than bins: nothing could ever be kept
+        seq.set_detector(100)
+    with pytest.raises(api.VisoError):          # more bins than pixels (viso.cpp:934)
+        seq.set_detector(600, 200, 5)
+    seq.set_detector(480)
+    with pytest.raises(api.VisoError):          # the bin layout is fixed once set
+        seq.set_detector(240)
+    seq.close()
+    with pytest.raises(api.VisoError):          # standalone: image too small
+        ctx.detect_harris(np.zeros((4, 4), np.uint8), 10, 1, 1)
+    big = np.zeros((600, 600), np.uint8)
+    with pytest.raises(api.VisoError) as e:     # one bin of 360 000 pixels does not fit in shared memory
+        ctx.detect_harris(big, 10, 1, 1)
+    assert e.value.code == -3
+    assert len(ctx.detect_harris(big, 0, 24, 5)) == 0    # n_features 0: nothing to do
