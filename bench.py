@@ -458,8 +458,15 @@ def main():
 
     # ---- max over ranks, gather records (the only collective: 64 B per frame pair) ----
     tms = torch.tensor([dev_ms, e2e_ms or 0.0, float(np.mean(match_ms))], dtype=torch.float64, device="cuda")
+    # every rank's own times and clocks (the sequences differ per rank, so does their work)
+    mine = torch.tensor([dev_ms / args.steps, (e2e_ms or 0.0) / args.steps, float(np.mean(match_ms)), float(sad_pairs),
+                         float(clocks.get("sm_mhz") or 0.0)], dtype=torch.float64, device="cuda")
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, mine)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    else:
+        per_rank = [mine]
     from libviso_b200.distributed import gather_records
     got = gather_records({rank: rec}, world, F, rank, world, device="cuda")   # sequence r lives on rank r
     all_rec = [got[s] for s in range(world)] if rank == 0 else None
@@ -476,6 +483,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16 SAD / f64 pose",
             "data": "synthetic", "config": workload_config(args),
             "clocks": clocks, "gpu_launches": int(launches),
+            "per_rank": {k: [round(float(t[i]), 3) for t in per_rank]
+                         for i, k in enumerate(("ms_per_step", "e2e_ms_per_step", "sad_ms", "sad_pairs", "sm_mhz"))},
             "roofline": {"bound": "hbm", "kernel": "sad_match_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args), "peak_source": peak_src,
                          "note": "HBM fraction as the contract defines it; the kernel is bound by the L1 data pipe (66% of peak "
