@@ -244,6 +244,9 @@ int viso_chain_poses(const viso_record* records, int n_frames, double* poses /* 
 int viso_seq_stats(viso_seq* seq, int64_t* match_bytes, int64_t* sad_pairs, int64_t* sad_evaluated);
 /* elapsed ms of the sad_match kernel in the last run (CUDA events on the context stream) */
 int viso_seq_match_ms(viso_seq* seq, float* ms);
+/* queries of the last submission that the tile kernel left to the generic kernel (top-K cut needed, candidate list or
+ * staging buffer too small): a performance diagnostic, results do not depend on it */
+int viso_seq_last_pending(viso_seq* seq, int32_t* n_pending);
 /* parity-test getters (host copies).  which: 0 = stereo (frame t), 1 = temporal left (t vs t-1), 2 = temporal right */
 int viso_seq_get_dense(viso_seq* seq, int which, int t, int32_t* out4 /* n x 4: idx,d1,d2,valid */, int32_t* n);
 /* packed descriptor rows (n x 128 u16, value + 1024, pad 0) of frame t; side 0 = left, 1 = right */

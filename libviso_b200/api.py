@@ -441,6 +441,11 @@ class Sequence:
         self.ctx._ck(lib().viso_seq_stats(self.h, C.byref(mb), C.byref(sp), C.byref(se)))
         return mb.value, sp.value, se.value
 
+    def last_pending(self):
+        n = C.c_int32(0)
+        self.ctx._ck(lib().viso_seq_last_pending(self.h, C.byref(n)))
+        return n.value
+
     def match_ms(self):
         ms = C.c_float(0)
         self.ctx._ck(lib().viso_seq_match_ms(self.h, C.byref(ms)))

@@ -368,7 +368,7 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
     CK(viso_launch_pack(b.pack, 2, std::max(n1, n2), dlen, b.err, s));
     CK(viso_launch_grid(b.grid, 2, ctx->grid, s));
     int ml = 0;
-    CK(viso_launch_match(b.match, 1, n1, n2, mp, ctx->grid, nullptr, b.pending, s, &ml));
+    CK(viso_launch_match(b.match, 1, n1, n2, mp, ctx->grid, nullptr, PendingList{b.pending, nullptr, nullptr, 0}, s, &ml));
     ctx->launches += 2 + ml;
     std::vector<int4> host_out;
     std::vector<int> host_m;

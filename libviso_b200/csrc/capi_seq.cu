@@ -12,6 +12,8 @@
 
 using namespace viso_capi;
 
+#define VISO_SEQ_PENDING_CAP 65536
+
 struct viso_seq {
     viso_ctx* ctx = nullptr;
     int F = 0, cap = 0, dlen = 0, maxH = 0, ncell = 0;
@@ -39,6 +41,8 @@ struct viso_seq {
     unsigned long long* pairs = nullptr;
     int* err = nullptr;
     int* pending = nullptr;
+    uint4* pend_rec = nullptr;            /* the queries the tile kernel left to the generic kernel (first 64 Ki) */
+    int* pend_job = nullptr;
     int *h_nL = nullptr, *h_nR = nullptr, *h_from_image = nullptr; /* pinned: truly asynchronous count uploads */
     int* from_image = nullptr;            /* device [F]: frame t's descriptors come from its images */
     unsigned char *imgL = nullptr, *imgR = nullptr;
@@ -123,7 +127,7 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     SA(hyp_ok, F * H); SA(hyp_count, F * H); SA(inliers, F * cap); SA(active, F * cap);
     SA(rec, F); SA(seeds, F * H * 3);
     SA(pack_jobs, 2 * F); SA(grid_jobs, 2 * F); SA(match_jobs, 3 * F); SA(sort_jobs, F); SA(circ_jobs, F); SA(probs, F);
-    SA(pairs, 2); SA(err, 1); SA(pending, 1); SA(from_image, F); SA(extract_jobs, 2 * F);
+    SA(pairs, 2); SA(err, 1); SA(pending, 1); SA(pend_rec, VISO_SEQ_PENDING_CAP); SA(pend_job, VISO_SEQ_PENDING_CAP); SA(from_image, F); SA(extract_jobs, 2 * F);
 #undef SA
     if (cudaMallocHost(&s->h_nL, 4 * F * sizeof(int)) != cudaSuccess) {
         seq_free(s);
@@ -529,7 +533,8 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
     /* match jobs: frame 0 has one (stereo), frame t >= 1 has three (stereo, temporal L, temporal R) */
     const int mj0 = t0 == 0 ? 0 : 3 * t0 - 2, mj1 = 3 * t1 - 2;
     CK(cudaEventRecord(s->ev0, st));
-    CK(viso_launch_match(s->match_jobs + mj0, mj1 - mj0, max_n, max_nt, mp, s->grid, s->pairs, s->pending, st, &nl));
+    CK(viso_launch_match(s->match_jobs + mj0, mj1 - mj0, max_n, max_nt, mp, s->grid, s->pairs,
+                         PendingList{s->pending, s->pend_rec, s->pend_job, VISO_SEQ_PENDING_CAP}, st, &nl));
     CK(cudaEventRecord(s->ev1, st));
     CK(viso_launch_sort(s->sort_jobs + t0, nf, max_nL, pd, st));
     ++nl;
@@ -631,6 +636,16 @@ int viso_seq_match_ms(viso_seq* s, float* ms)
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(s->ev1));
     CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    return VISO_OK;
+}
+
+int viso_seq_last_pending(viso_seq* s, int32_t* n_pending)
+{
+    if (!s || !n_pending) return VISO_ERR_ARG;
+    viso_ctx* ctx = s->ctx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(n_pending, s->pending, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return VISO_OK;
 }
 

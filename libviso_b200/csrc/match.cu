@@ -666,6 +666,12 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
     return pairs;
 }
 
+__device__ __forceinline__ void pend_push(const PendingList& pend, const uint4& qrec, int job_index)
+{
+    const int slot = atomicAdd(pend.count, 1);
+    if (slot < pend.cap) { pend.rec[slot] = qrec; pend.job[slot] = job_index; }
+}
+
 /*
  * sad_match_kernel: match_desc (viso.cpp:668-722) for a batch of jobs.  blockIdx.y = job, blockIdx.x = query tile
  * (VISO_TILE_W x VISO_TILE_H cells of the QUERY set's grid, 96 x 64 px).
@@ -685,7 +691,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
  */
 __global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, VISO_MATCH_MINB)
 sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, int reg_cap, int ql_cap,
-                 unsigned long long* sad_pairs, int* n_pending)
+                 unsigned long long* sad_pairs, PendingList pend)
 {
     extern __shared__ uint4 reg[];                                /* staged neighbourhood, reg_cap records */
     /* per-query candidate lists (region indices), 32 x (ql_cap + 2): the +2 makes the word stride odd so that
@@ -785,8 +791,11 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
 
     unsigned pairs = 0;
     if (!tile_ok) { /* leave the whole tile to the generic kernel */
-        for (int k = threadIdx.x; k < qtot; k += blockDim.x) job.out[query_rec(k).z] = make_int4(0, 0, 0, VISO_PENDING);
-        if (threadIdx.x == 0) atomicAdd(n_pending, qtot);
+        for (int k = threadIdx.x; k < qtot; k += blockDim.x) {
+            const uint4 qr = query_rec(k);
+            job.out[qr.z] = make_int4(0, 0, 0, VISO_PENDING);
+            pend_push(pend, qr, blockIdx.y);
+        }
     } else {
         const int R = tile_s[3];
         for (int rr = warp; rr < nrows; rr += VISO_MATCH_WARPS) {
@@ -827,7 +836,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 if (n > ql_cap || n > P.K) { /* top-K cut or list overflow: left to the generic kernel */
                     if (lane == 0) {
                         job.out[qrec.z] = make_int4(0, 0, 0, VISO_PENDING);
-                        atomicAdd(n_pending, 1);
+                        pend_push(pend, qrec, blockIdx.y);
                     }
                     continue;
                 }
@@ -877,26 +886,36 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
  */
 __global__ void __launch_bounds__(VISO_MATCH_WARPS * 32)
 sad_match_generic_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, unsigned long long* sad_pairs,
-                         const int* __restrict__ n_pending, int only_pending)
+                         PendingList pend, int only_pending)
 {
     __shared__ WarpScratch wscr[VISO_MATCH_WARPS];
-    if (only_pending && *n_pending == 0) return;
-    const MatchJob job = jobs[blockIdx.y];
-    const MatchParamsDev& P = mp.p[job.mode];
-    const int nq = *job.q.n, nt = *job.t.n;
+    const int np = only_pending ? *pend.count : 0;
+    if (only_pending && np == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch& ws = wscr[warp];
     unsigned pairs = 0;
-    for (int chunk = blockIdx.x; chunk * VISO_STRIP_QPC < nq; chunk += gridDim.x)
-    for (int qi = chunk * VISO_STRIP_QPC + warp; qi < min(nq, (chunk + 1) * VISO_STRIP_QPC); qi += VISO_MATCH_WARPS) {
-        const uint4 qrec = __ldg(job.q.srec + qi);
-        if (only_pending && job.out[qrec.z].w != VISO_PENDING) continue;
-        if (nt <= 0) {
+    auto one_query = [&](const MatchJob& job, const uint4& qrec) {
+        const MatchParamsDev& P = mp.p[job.mode];
+        if (*job.t.n <= 0) {
             if (lane == 0) job.out[qrec.z] = make_int4(-1, INT_MAX, INT_MAX, 0);
-            continue;
+            return;
         }
         GlobalVisitor vis{job.t, g, make_geom(g, __uint_as_float(qrec.x), __uint_as_float(qrec.y), P.radius), ws, lane, 0, true};
         pairs += match_query(vis, job, P, ws, lane, qrec);
+    };
+    if (only_pending && pend.rec && np <= pend.cap) {
+        /* the listed queries, spread over all CTAs of the grid (entry e goes to CTA e mod #CTAs) */
+        const int cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
+        for (int e = cta + warp * ncta; e < np; e += ncta * VISO_MATCH_WARPS) one_query(jobs[pend.job[e]], pend.rec[e]);
+    } else {
+        const MatchJob job = jobs[blockIdx.y];
+        const int nq = *job.q.n;
+        for (int chunk = blockIdx.x; chunk * VISO_STRIP_QPC < nq; chunk += gridDim.x)
+            for (int qi = chunk * VISO_STRIP_QPC + warp; qi < min(nq, (chunk + 1) * VISO_STRIP_QPC); qi += VISO_MATCH_WARPS) {
+                const uint4 qrec = __ldg(job.q.srec + qi);
+                if (only_pending && job.out[qrec.z].w != VISO_PENDING) continue;
+                one_query(job, qrec);
+            }
     }
     if (sad_pairs && lane == 0 && pairs) {
         atomicAdd(sad_pairs, (unsigned long long)pairs);
@@ -948,7 +967,7 @@ cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStr
 }
 
 cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
-                              GridCfg g, unsigned long long* sad_pairs, int* n_pending, cudaStream_t s, int* launches)
+                              GridCfg g, unsigned long long* sad_pairs, PendingList pend, cudaStream_t s, int* launches)
 {
     if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
     static int mode = -1;
@@ -960,7 +979,7 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
     const int gchunks = (max_nq + VISO_STRIP_QPC - 1) / VISO_STRIP_QPC;
     const dim3 ggrid(std::min(gchunks, std::max(1, (148 * 16 + n_jobs - 1) / n_jobs)), n_jobs);
     if (mode == 1) {
-        sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, n_pending, 0);
+        sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, pend, 0);
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
@@ -989,13 +1008,13 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
     }
     /* a kernel, not cudaMemsetAsync: memsets and copies on the compute stream can be scheduled on a copy engine and
      * then wait behind every upload queued there (see viso_seq_run_range) */
-    cudaError_t e = viso_launch_zero(n_pending, 1, s);
+    cudaError_t e = viso_launch_zero(pend.count, 1, s);
     if (e != cudaSuccess) return e;
     const int tiles = ((g.gx + VISO_TILE_W - 1) / VISO_TILE_W) * ((g.gy + VISO_TILE_H - 1) / VISO_TILE_H);
-    sad_match_kernel<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, ql_cap, sad_pairs, n_pending);
+    sad_match_kernel<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, ql_cap, sad_pairs, pend);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, n_pending, 1);
+    sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, pend, 1);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

@@ -183,8 +183,16 @@ size_t viso_harris_cells(const HarrisCfg& c);   /* response slots a bin occupies
 cudaError_t viso_launch_detect(const DetectJob* jobs, int n_jobs, const HarrisCfg& c, cudaStream_t s);
 cudaError_t viso_launch_zero(void* p, int n_words, cudaStream_t s);   /* a few words, by a kernel */
 cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStream_t s);
+/* queries the tile kernel leaves to the generic kernel: a counter and (optionally) the list of the first `cap` of them,
+ * (job index, cell-sorted query record); without a list, or when it overflows, the generic kernel scans every query */
+struct PendingList {
+    int* count;
+    uint4* rec;
+    int* job;
+    int cap;
+};
 cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
-                              GridCfg g, unsigned long long* sad_pairs, int* n_pending, cudaStream_t s, int* launches);
+                              GridCfg g, unsigned long long* sad_pairs, PendingList pend, cudaStream_t s, int* launches);
 cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, int max_n, ParamDev p, cudaStream_t s);
 cudaError_t viso_launch_circle(const CircleJob* jobs, int n_jobs, cudaStream_t s);
 cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, int max_n, ParamDev p, cudaStream_t s,

@@ -779,3 +779,40 @@ def test_detector_argument_errors(ctx, api):
         ctx.detect_harris(big, 10, 1, 1)
     assert e.value.code == -3
     assert len(ctx.detect_harris(big, 0, 24, 5)) == 0    # n_features 0: nothing to do
+
+
+@pytest.mark.gpu
+def test_sequence_with_dense_clusters_uses_the_pending_list(ctx, api, oracle, small_sequence):
+    """a dense blob of keypoints in every frame overflows the tile kernel's per-query candidate lists; those queries
+    are handed to the generic kernel through the pending list -- same results as the oracle"""
+    from libviso_b200 import synth
+    frames, _ = small_sequence
+    rng = np.random.default_rng(31)
+    P1, P2 = synth.kitti_calib()
+    H = 50
+    dense = []
+    for t, f in enumerate(frames[:4]):
+        cells = rng.choice(24 * 24, 160, replace=False)
+        blob = np.stack([600 + cells % 24 + 2 * t, 150 + cells // 24], 1).astype(np.float32)
+        g = dict(f)
+        for side, im in (("L", f["imL"]), ("R", f["imR"])):
+            kp = np.concatenate([f["kp" + side], blob - (np.array([9, 0], np.float32) if side == "R" else 0)])
+            g["kp" + side] = kp
+            g["d" + side] = oracle.extract_descriptors(oracle.sobel_x(im), kp)
+        dense.append(g)
+    seeds = make_seeds(len(dense), H)
+    o = oracle.sequence(dense, P1, P2, oracle.param_default(ransac_iter=H), seeds, dump=True)
+    cap = max(max(len(f["kpL"]), len(f["kpR"])) for f in dense)
+    seq = ctx.sequence(len(dense), cap, 121, H)
+    seq.set_calib(P1, P2)
+    seq.upload(dense)
+    seq.run(api.param_default(ransac_iter=H), seeds)
+    rec = seq.download()
+    assert seq.last_pending() > 50
+    for t in range(1, len(dense)):
+        assert np.array_equal(seq.get_dense(1, t), o["m11"][t]), t
+        assert np.array_equal(seq.get_dense(2, t), o["m22"][t]), t
+    for k in ("ok", "n_inliers", "n_circ", "best_hyp"):
+        assert np.array_equal(rec[k], o["records"][k]), k
+    assert_tr_close(rec["tr"], o["records"]["tr"])
+    seq.close()
