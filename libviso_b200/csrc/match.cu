@@ -999,12 +999,9 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
     int ql_cap = (int)fmin(256.0, fmax(64.0, 1.5 * in_diamond + 16.0));
     ql_cap = (ql_cap + 31) & ~31;
     const size_t smem = (size_t)cap * sizeof(uint4) + (size_t)32 * (ql_cap + 2) * sizeof(unsigned short);
-    static int attr_set = 0;
-    if (smem > 24 * 1024 && !attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             6144 * 16 + 32 * 258 * 2);
+    if (smem > 48 * 1024) { /* per device, so set whenever it is needed (a process may drive several GPUs) */
+        cudaError_t e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = 1;
     }
     /* a kernel, not cudaMemsetAsync: memsets and copies on the compute stream can be scheduled on a copy engine and
      * then wait behind every upload queued there (see viso_seq_run_range) */
