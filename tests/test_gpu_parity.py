@@ -816,3 +816,35 @@ def test_sequence_with_dense_clusters_uses_the_pending_list(ctx, api, oracle, sm
         assert np.array_equal(rec[k], o["records"][k]), k
     assert_tr_close(rec["tr"], o["records"]["tr"])
     seq.close()
+
+
+@pytest.mark.gpu
+def test_sequence_pending_list_overflow_falls_back_to_the_scan(ctx, api, oracle):
+    """9 frames of 3000 keypoints packed into 400 x 300 px: every query has more than max_neighbors points in range, so
+    all 75 000 queries of the 25 match jobs are left to the generic kernel -- more than the pending list holds, which
+    switches the generic kernel to its scan over all queries.  Matches against the oracle, bit for bit."""
+    from libviso_b200 import synth
+    rng = np.random.default_rng(41)
+    P1, P2 = synth.kitti_calib()
+    H, F, n = 10, 9, 3000
+    frames = []
+    for t in range(F):
+        kl, dl = random_features(rng, n, 400, 300)
+        kr, dr = random_features(rng, n, 400, 300)
+        frames.append(dict(kpL=kl, kpR=kr, dL=dl, dR=dr))
+    seeds = make_seeds(F, H)
+    o = oracle.sequence(frames, P1, P2, oracle.param_default(ransac_iter=H), seeds, dump=True)
+    seq = ctx.sequence(F, n, 121, H)
+    seq.set_calib(P1, P2)
+    seq.upload(frames)
+    seq.run(api.param_default(ransac_iter=H), seeds)
+    rec = seq.download()
+    assert seq.last_pending() > 65536
+    for t in range(F):
+        assert np.array_equal(seq.get_lr_matches(t), o["lr_matches"][t]), t
+        if t:
+            assert np.array_equal(seq.get_dense(1, t), o["m11"][t]), t
+            assert np.array_equal(seq.get_dense(2, t), o["m22"][t]), t
+    for k in ("ok", "n_inliers", "n_circ", "best_hyp"):
+        assert np.array_equal(rec[k], o["records"][k]), k
+    seq.close()
