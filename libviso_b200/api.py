@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libviso_b200.so")
+SO_PATH = os.environ.get("VISO_B200_LIB") or os.path.join(_HERE, "libviso_b200.so")   # override: tuning builds only
 
 VISO_OK = 0
 ERR_NAMES = {-1: "VISO_ERR_CUDA", -2: "VISO_ERR_ARG", -3: "VISO_ERR_DOMAIN", -4: "VISO_ERR_DIV0",
