@@ -494,7 +494,12 @@ def main():
                          "algorithmic_bytes_per_launch": int(match_bytes), "kernel_ms": mm,
                          "sad_pairs_per_launch": int(sad_pairs), "queries_left_to_generic_kernel": int(n_pending), "sad_evaluated_per_launch": int(sad_eval),
                          "kernel_share_of_step": mm / (dev_ms / args.steps)},
-            "poses": {"chained_per_sequence": n_poses, "ok_frame_pairs": int(sum(int(r["ok"].sum()) for r in all_rec))},
+            "poses": {"chained_per_sequence": n_poses, "ok_frame_pairs": int(sum(int(r["ok"].sum()) for r in all_rec)),
+                      "circular_matches_mean": float(np.mean([r["n_circ"][1:].mean() for r in all_rec])),
+                      "inliers_mean": float(np.mean([r["n_inliers"][1:].mean() for r in all_rec])),
+                      # RANSAC scoring work of one launch on rank 0: hypotheses x circular matches, 38 flops each
+                      # (SURVEY 8d); FP64 rates to hold it against: tools/ubench_fp64.cu
+                      "ransac_point_tests_per_launch": int(args.hyp * int(all_rec[0]["n_circ"][1:].sum()))},
         }
         if e2e_ms is not None:
             line["e2e"] = {"value": world * n_pairs * args.steps / (e2e_ms_g * 1e-3), "unit": "frame-pairs/s",
