@@ -494,9 +494,11 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
     /* everything uploaded so far (frames, seeds, counts) is visible to the kernels below */
     CK(cudaEventRecord(s->ev_copy, ctx->copy_stream));
     CK(cudaStreamWaitEvent(st, s->ev_copy, 0));
+    int nl = 0;
     if (t0 == 0) {
         CK(viso_launch_zero(s->pairs, 4, st));
         CK(viso_launch_zero(s->err, 1, st));
+        nl += 2;
     }
     int max_n = 0, max_nL = 0, any_img = 0, any_f32 = 0, any_det = 0;
     for (int t = t0; t < t1; ++t) {
@@ -517,7 +519,6 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
     mp.p[0] = make_match_dev(&ms);
     mp.p[1] = make_match_dev(&mt);
 
-    int nl = 0;
     if (any_f32 && max_n > 0) { CK(viso_launch_pack(s->pack_jobs + 2 * t0, 2 * nf, max_n, s->dlen, s->err, st)); ++nl; }
     if (any_det) {
         /* overwrites the counts copied above with the detector's own */

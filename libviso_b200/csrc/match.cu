@@ -1012,6 +1012,6 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, pend, 1);
-    if (launches) *launches += 2;
+    if (launches) *launches += 3; /* zero_words, tile kernel, generic kernel */
     return cudaGetLastError();
 }
