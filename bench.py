@@ -144,7 +144,7 @@ def ncu_traffic(args):
     return None
 
 
-def cpu_oracle_pairs(frames, order, t0, n_pairs, H, seeds):
+def cpu_oracle_pairs(frames, order, t0, n_pairs, H, seeds, front_end=0):
     """run the CPU oracle over frames [t0, t0+n_pairs] of the long sequence; returns (seconds, records)"""
     from oracle import oracle
     from libviso_b200 import synth
@@ -153,6 +153,11 @@ def cpu_oracle_pairs(frames, order, t0, n_pairs, H, seeds):
     param = oracle.param_default(ransac_iter=H)
     sd = np.ascontiguousarray(seeds[t0:t0 + n_pairs + 1])
     t = time.perf_counter()
+    if front_end:
+        # --input raw: the reference's front end per frame too (viso.cpp:1226-1231), with OpenCV doing what the
+        # reference asks OpenCV to do (cv::cornerHarris, cv::Sobel) -- the oracle's own scalar detector would be an
+        # unfairly slow stand-in
+        sub = [synth.make_features(f["imL"], f["imR"], front_end) for f in sub]
     out = oracle.sequence(sub, P1, P2, param, sd)
     return time.perf_counter() - t, out["records"]
 
@@ -174,7 +179,7 @@ def run_reference(args, rank, world, guard):
     pairs_per_proc = 6
     jobs_per_step = cores
     global _REF_STATE
-    _REF_STATE = (frames, order, seeds, args.hyp)
+    _REF_STATE = (frames, order, seeds, args.hyp, args.features if args.input == "raw" else 0)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         def step(i):
@@ -190,6 +195,8 @@ def run_reference(args, rank, world, guard):
     value = n_pairs / total
     sample = (f"{jobs_per_step} processes x {pairs_per_proc} frame pairs per step, independent frame ranges of the same "
               f"{args.frames}-frame sequence")
+    if args.input == "raw":
+        sample += "; front end per frame = cv2.cornerHarris + cv2.Sobel + numpy binning / patch gather (libviso_b200/synth.py)"
     line = {
         "impl": "reference", "metric": "frame-pairs/s (match+RANSAC pose) at 1241x376", "value": value,
         "unit": "frame-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -208,8 +215,8 @@ _REF_STATE = None
 
 def _ref_step(job):
     t0, n_pairs = job
-    frames, order, seeds, H = _REF_STATE
-    return cpu_oracle_pairs(frames, order, t0, n_pairs, H, seeds)[0]
+    frames, order, seeds, H, front_end = _REF_STATE
+    return cpu_oracle_pairs(frames, order, t0, n_pairs, H, seeds, front_end)[0]
 
 
 def workload_config(args):

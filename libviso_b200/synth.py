@@ -163,13 +163,18 @@ def extract_descriptors(img, kp, radius=5):
     return np.ascontiguousarray(d.reshape(len(kp), -1), dtype=np.float32)
 
 
+def make_features(imL, imR, n_features):
+    """the reference's front end on one stereo pair (viso.cpp:1226-1231) with OpenCV's cornerHarris and Sobel"""
+    kpL = detect_harris_binned(imL, n_features)
+    kpR = detect_harris_binned(imR, n_features)
+    return dict(kpL=kpL, kpR=kpR, dL=extract_descriptors(imL, kpL), dR=extract_descriptors(imR, kpR), imL=imL, imR=imR)
+
+
 def make_frame(pose, tex, n_features, noise_rng):
     R, p = pose
     imL = render(R, p, tex, noise_rng)
     imR = render(R, p + R @ np.array([BASE, 0.0, 0.0]), tex, noise_rng)
-    kpL = detect_harris_binned(imL, n_features)
-    kpR = detect_harris_binned(imR, n_features)
-    return dict(kpL=kpL, kpR=kpR, dL=extract_descriptors(imL, kpL), dR=extract_descriptors(imR, kpR), imL=imL, imR=imR)
+    return make_features(imL, imR, n_features)
 
 
 def _seq_worker(args):
