@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
  * sum.  The image is touched once per frame, so the loads mostly miss to DRAM: a warp issues the loads of
  * VISO_EXTRACT_ROUNDS x 2 keypoints before using any.
  */
+#ifndef VISO_EXTRACT_ROUNDS
 #define VISO_EXTRACT_ROUNDS 2
+#endif
 
 __device__ __forceinline__ int reflect101(int i, int n)
 {
