@@ -500,7 +500,12 @@ def main():
                                  "wavefronts in the committed ncu capture) and the ALU pipe (51%), not by HBM: DESIGN.md section 4",
                          "algorithmic_bytes_per_launch": int(match_bytes), "kernel_ms": mm,
                          "sad_pairs_per_launch": int(sad_pairs), "queries_left_to_generic_kernel": int(n_pending), "sad_evaluated_per_launch": int(sad_eval),
-                         "kernel_share_of_step": mm / (dev_ms / args.steps)},
+                         "kernel_share_of_step": mm / (dev_ms / args.steps),
+                         # the roof of the kernel's own access pattern: the same row gather without arithmetic,
+                         # measured once on B200 by tools/ubench_rowgather.cu (profiles/r01_e_rowgather_roof.txt)
+                         "gather_roof": {"rows_per_s": 80.1e9, "achieved_rows_per_s": sad_pairs / (mm * 1e-3),
+                                         "frac": sad_pairs / (mm * 1e-3) / 80.1e9,
+                                         "source": "tools/ubench_rowgather.cu, measured on B200 in round 1 (not re-measured by this run)"}},
             "poses": {"chained_per_sequence": n_poses, "ok_frame_pairs": int(sum(int(r["ok"].sum()) for r in all_rec)),
                       "circular_matches_mean": float(np.mean([r["n_circ"][1:].mean() for r in all_rec])),
                       "inliers_mean": float(np.mean([r["n_inliers"][1:].mean() for r in all_rec])),
