@@ -817,14 +817,18 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 if (warp == 0) qrec_s[lane] = qr;
                 const float qx = __uint_as_float(qr.x), qy = __uint_as_float(qr.y);
                 const float d0 = l1_dist(qx, qy, t0.x, t0.y);
-                /* limit = min(radius, strictly below D0): candidates need dist <= r and dist < D0 (index-0 rule) */
-                const float D0 = (d0 <= r) ? d0 : CUDART_INF_F;
+                /* candidates need dist <= r and dist < D0 (index-0 rule), D0 = d0 if d0 <= r: one strict comparison
+                 * against lim = min(next float above r, D0); lanes without a query get lim = -inf */
+                /* the next float above r (r >= 0; an infinite radius stays infinite; a negative one only moves
+                 * further below every distance) */
+                const float r_up = r < CUDART_INF_F ? __uint_as_float(__float_as_uint(r) + 1u) : r;
+                const float lim = act ? ((d0 <= r) ? d0 : r_up) : -CUDART_INF_F;
                 const float2* pts = reinterpret_cast<const float2*>(reg);
 #pragma unroll 4
                 for (int i = warp; i < R; i += VISO_MATCH_WARPS) {
                     const float2 p = pts[2 * i]; /* (x, y) of the uint4 record: broadcast */
                     const float dist = l1_dist(qx, qy, p.x, p.y);
-                    if (act && dist <= r && dist < D0) {
+                    if (dist < lim) {
                         const int j = atomicAdd(&qcnt[lane], 1);
                         if (j < ql_cap) qlist[lane * ql_stride + j] = (unsigned short)i;
                     }
