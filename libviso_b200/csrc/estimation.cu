@@ -182,7 +182,12 @@ __device__ __forceinline__ void sample_from_seeds(const uint32_t* seeds, int N, 
 __constant__ int c_pair_a[27] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 0, 1, 2, 3, 4, 5};
 __constant__ int c_pair_b[27] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 6, 6, 6, 6, 6, 6};
 
+#ifndef VISO_HYP_PER_CTA
 #define VISO_HYP_PER_CTA 32 /* hypotheses per CTA of ransac_hyp_kernel: 4 lanes each */
+#endif
+#ifndef VISO_HYP_MINB
+#define VISO_HYP_MINB 1
+#endif
 
 /*
  * FOUR LANES per hypothesis: tr = 0, 3-point sample, Gauss-Newton (minimize_reproj with 3 active points),
@@ -197,7 +202,7 @@ __constant__ int c_pair_b[27] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3,
  *               to cv::mulTransposed / J^T r);
  *   lane 0      the LU solve and the convergence test (viso.cpp:1602-1617), broadcast by shuffle.
  */
-__global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4) ransac_hyp_kernel(const RansacProb* __restrict__ probs, ParamDev P)
+__global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4, VISO_HYP_MINB) ransac_hyp_kernel(const RansacProb* __restrict__ probs, ParamDev P)
 {
     __shared__ double rows_s[VISO_HYP_PER_CTA][12][7];
     __shared__ double sums_s[VISO_HYP_PER_CTA][28];
