@@ -90,6 +90,11 @@ int viso_share_copy_stream(viso_ctx* ctx, viso_ctx* owner);
 /* extent of the uniform candidate grid (pixels); coordinates outside are clamped into border cells, so any
  * value is correct, a matching one is fast.  Default 1248 x 384. */
 int viso_set_image_extent(viso_ctx* ctx, int width, int height);
+/* Which kernel path match_desc runs through (results are identical; tests and A/B measurements force one):
+ * 0 auto (descriptor rows of a query tile's neighbourhood staged in shared memory when they fit, else gathered
+ * through L1), 1 generic per-query kernel only, 2 gather tile kernel, 3 staged tile kernel.  The environment
+ * variable VISO_MATCH_MODE = generic | gather | staged sets the initial value at viso_create. */
+int viso_set_match_mode(viso_ctx* ctx, int mode);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 int64_t viso_launch_count(const viso_ctx* ctx);
 /* CUDA-event stopwatch on the context stream: begin records an event; end records a second one, waits for it and

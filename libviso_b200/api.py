@@ -186,6 +186,12 @@ class Context:
     def set_image_extent(self, w, h):
         self._ck(lib().viso_set_image_extent(self.h, int(w), int(h)))
 
+    MATCH_MODES = {"auto": 0, "generic": 1, "gather": 2, "staged": 3}
+
+    def set_match_mode(self, mode):
+        """force one kernel path of match_desc ("auto", "generic", "gather", "staged"); results are identical"""
+        self._ck(lib().viso_set_match_mode(self.h, self.MATCH_MODES[mode] if isinstance(mode, str) else int(mode)))
+
     def launch_count(self):
         return int(lib().viso_launch_count(self.h))
 

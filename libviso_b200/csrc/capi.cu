@@ -175,7 +175,20 @@ int viso_create(viso_ctx** out, int device)
         return VISO_ERR_CUDA;
     }
     ctx->own_copy_stream = ctx->copy_stream;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
+    if (const char* m = getenv("VISO_MATCH_MODE")) /* generic | gather | staged: force one matching path (tests, A/B) */
+        ctx->match_mode = m[0] == 'g' && m[1] == 'e' ? VISO_MATCH_GENERIC : m[0] == 'g' ? VISO_MATCH_GATHER
+                          : m[0] == 's' ? VISO_MATCH_STAGED : VISO_MATCH_AUTO;
     *out = ctx;
+    return VISO_OK;
+}
+
+int viso_set_match_mode(viso_ctx* ctx, int mode)
+{
+    if (!ctx) return VISO_ERR_ARG;
+    if (mode < VISO_MATCH_AUTO || mode > VISO_MATCH_STAGED) return ctx->fail(VISO_ERR_ARG, "set_match_mode: unknown mode");
+    ctx->match_mode = mode;
     return VISO_OK;
 }
 
@@ -305,7 +318,7 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
     struct Bufs {
         float2 *xy1, *xy2;
         uint4 *srec1, *srec2;
-        unsigned *rs1, *rs2;
+        int *po1, *po2;
         float *df1, *df2;
         uint16_t *du1, *du2;
         int *cell1, *cell2, *counts, *err, *matches, *mcount;
@@ -320,7 +333,7 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
     auto carve = [&](Carver& c) {
         b.xy1 = c.take<float2>(n1); b.xy2 = c.take<float2>(n2);
         b.srec1 = c.take<uint4>(n1); b.srec2 = c.take<uint4>(n2);
-        b.rs1 = c.take<unsigned>(n1); b.rs2 = c.take<unsigned>(n2);
+        b.po1 = c.take<int>(n1); b.po2 = c.take<int>(n2);
         b.df1 = c.take<float>((size_t)n1 * dlen); b.df2 = c.take<float>((size_t)n2 * dlen);
         b.du1 = c.take<uint16_t>((size_t)n1 * VISO_DESC_U16); b.du2 = c.take<uint16_t>((size_t)n2 * VISO_DESC_U16);
         b.cell1 = c.take<int>(ncell + 1); b.cell2 = c.take<int>(ncell + 1);
@@ -348,11 +361,11 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
         CK(cudaMemcpyAsync(b.xy2, kp2, (size_t)n2 * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(b.df2, d2, (size_t)n2 * dlen * 4, cudaMemcpyHostToDevice, s));
     }
-    PackJob pj[2] = {{b.df1, b.counts, b.du1, b.rs1, nullptr}, {b.df2, b.counts + 1, b.du2, b.rs2, nullptr}};
-    GridJob gj[2] = {{b.xy1, b.counts, b.rs1, b.srec1, b.cell1}, {b.xy2, b.counts + 1, b.rs2, b.srec2, b.cell2}};
+    PackJob pj[2] = {{b.df1, b.counts, b.du1, b.srec1, nullptr}, {b.df2, b.counts + 1, b.du2, b.srec2, nullptr}};
+    GridJob gj[2] = {{b.xy1, b.counts, b.po1, b.srec1, b.cell1}, {b.xy2, b.counts + 1, b.po2, b.srec2, b.cell2}};
     MatchJob mj;
-    mj.q = SetView{b.xy1, b.counts, b.du1, b.srec1, b.cell1};
-    mj.t = SetView{b.xy2, b.counts + 1, b.du2, b.srec2, b.cell2};
+    mj.q = SetView{b.xy1, b.counts, b.du1, b.srec1, b.cell1, b.po1};
+    mj.t = SetView{b.xy2, b.counts + 1, b.du2, b.srec2, b.cell2, b.po2};
     mj.out = b.out; mj.mode = 0; mj.pad = 0;
     SortJob sj;
     sj.dense = b.out; sj.n = b.counts; sj.kp1 = b.xy1; sj.kp2 = b.xy2; sj.matches = b.matches; sj.count = b.mcount;
@@ -365,10 +378,11 @@ static int match_desc_impl(viso_ctx* ctx, const float* kp1, int n1, const float*
     MatchParamsPair mp;
     mp.p[0] = make_match_dev(params);
     mp.p[1] = mp.p[0];
-    CK(viso_launch_pack(b.pack, 2, std::max(n1, n2), dlen, b.err, s));
     CK(viso_launch_grid(b.grid, 2, ctx->grid, s));
+    CK(viso_launch_pack(b.pack, 2, std::max(n1, n2), dlen, b.err, s)); /* rows in cell-sorted order: after the grid */
     int ml = 0;
-    CK(viso_launch_match(b.match, 1, n1, n2, mp, ctx->grid, nullptr, PendingList{b.pending, nullptr, nullptr, 0}, s, &ml));
+    CK(viso_launch_match(b.match, 1, n1, n2, mp, ctx->grid, nullptr, PendingList{b.pending, nullptr, nullptr, 0},
+                         ctx->match_mode, ctx->sm_count, s, &ml));
     ctx->launches += 2 + ml;
     std::vector<int4> host_out;
     std::vector<int> host_m;
@@ -1021,7 +1035,7 @@ int viso_extract_descriptors(viso_ctx* ctx, const uint8_t* img, int width, int h
     carve(real);
     cudaStream_t s = ctx->stream;
     const int one = 1;
-    const ExtractJob job{b.img, b.kp, b.n, b.rows, b.rsum, b.flag};
+    const ExtractJob job{b.img, b.kp, b.n, b.rows, b.rsum, nullptr, b.flag};
     CK(cudaMemcpyAsync(b.img, img, (size_t)pitch * height, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(b.kp, kp_xy, (size_t)n * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(b.n, &n, 4, cudaMemcpyHostToDevice, s));

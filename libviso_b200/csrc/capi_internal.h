@@ -23,6 +23,8 @@ struct viso_ctx {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaStream_t copy_stream = nullptr;   /* host -> device uploads of sequence objects (overlap with compute) */
     cudaStream_t own_copy_stream = nullptr; /* the one this context created (copy_stream may be another context's) */
+    int match_mode = VISO_MATCH_AUTO;     /* VISO_MATCH_* (viso_dev.h): which matching kernel path; VISO_MATCH_MODE at viso_create */
+    int sm_count = 148;                   /* cudaDevAttrMultiProcessorCount of the device */
 
     int fail(int code, const std::string& msg)
     {

@@ -20,7 +20,7 @@ struct viso_seq {
     GridCfg grid{};
     float2 *kpL = nullptr, *kpR = nullptr;
     uint4 *srecL = nullptr, *srecR = nullptr;
-    unsigned *rsL = nullptr, *rsR = nullptr;
+    int *posL = nullptr, *posR = nullptr;   /* original index -> cell-sorted position */
     float *dLf = nullptr, *dRf = nullptr;
     uint16_t *dLu = nullptr, *dRu = nullptr;
     int *nL = nullptr, *nR = nullptr, *cellL = nullptr, *cellR = nullptr;
@@ -115,7 +115,7 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
         }                                                                                \
     } while (0)
     SA(kpL, F * cap); SA(kpR, F * cap); SA(srecL, F * cap); SA(srecR, F * cap);
-    SA(rsL, F * cap); SA(rsR, F * cap);
+    SA(posL, F * cap); SA(posR, F * cap);
     SA(dLf, F * cap * desc_len); SA(dRf, F * cap * desc_len);
     SA(dLu, F * cap * VISO_DESC_U16); SA(dRu, F * cap * VISO_DESC_U16);
     SA(nL, F); SA(nR, F); SA(cellL, F * nc); SA(cellR, F * nc);
@@ -162,19 +162,19 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     s->h_probs.resize(F);
     auto viewL = [&](size_t t) {
         return SetView{s->kpL + t * cap, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->srecL + t * cap,
-                       s->cellL + t * nc};
+                       s->cellL + t * nc, s->posL + t * cap};
     };
     auto viewR = [&](size_t t) {
         return SetView{s->kpR + t * cap, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->srecR + t * cap,
-                       s->cellR + t * nc};
+                       s->cellR + t * nc, s->posR + t * cap};
     };
     for (size_t t = 0; t < F; ++t) {
-        pj[2 * t] = PackJob{s->dLf + t * cap * desc_len, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->rsL + t * cap,
+        pj[2 * t] = PackJob{s->dLf + t * cap * desc_len, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->srecL + t * cap,
                             s->from_image + t};
-        pj[2 * t + 1] = PackJob{s->dRf + t * cap * desc_len, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->rsR + t * cap,
+        pj[2 * t + 1] = PackJob{s->dRf + t * cap * desc_len, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->srecR + t * cap,
                                 s->from_image + t};
-        gj[2 * t] = GridJob{s->kpL + t * cap, s->nL + t, s->rsL + t * cap, s->srecL + t * cap, s->cellL + t * nc};
-        gj[2 * t + 1] = GridJob{s->kpR + t * cap, s->nR + t, s->rsR + t * cap, s->srecR + t * cap, s->cellR + t * nc};
+        gj[2 * t] = GridJob{s->kpL + t * cap, s->nL + t, s->posL + t * cap, s->srecL + t * cap, s->cellL + t * nc};
+        gj[2 * t + 1] = GridJob{s->kpR + t * cap, s->nR + t, s->posR + t * cap, s->srecR + t * cap, s->cellR + t * nc};
         MatchJob m;
         m.pad = 0;
         m.q = viewL(t); m.t = viewR(t); m.out = s->dense_lr + t * cap; m.mode = 0; /* stereo, viso.cpp:1240 */
@@ -294,9 +294,9 @@ int viso_seq_set_image_size(viso_seq* s, int width, int height)
     std::vector<ExtractJob> ej(2 * F);
     for (size_t t = 0; t < F; ++t) {
         ej[2 * t] = ExtractJob{s->imgL + 2 * t * bytes, s->kpL + t * cap, s->nL + t, s->dLu + t * cap * VISO_DESC_U16,
-                               s->rsL + t * cap, s->from_image + t};
+                               nullptr, s->srecL + t * cap, s->from_image + t};
         ej[2 * t + 1] = ExtractJob{s->imgR + 2 * t * bytes, s->kpR + t * cap, s->nR + t, s->dRu + t * cap * VISO_DESC_U16,
-                                   s->rsR + t * cap, s->from_image + t};
+                                   nullptr, s->srecR + t * cap, s->from_image + t};
     }
     CK(cudaMemcpyAsync(s->extract_jobs, ej.data(), ej.size() * sizeof(ExtractJob), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -519,23 +519,25 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
     mp.p[0] = make_match_dev(&ms);
     mp.p[1] = make_match_dev(&mt);
 
-    if (any_f32 && max_n > 0) { CK(viso_launch_pack(s->pack_jobs + 2 * t0, 2 * nf, max_n, s->dlen, s->err, st)); ++nl; }
     if (any_det) {
         /* overwrites the counts copied above with the detector's own */
         CK(viso_launch_detect(s->detect_jobs + 2 * t0, 2 * nf, s->hc, st));
         nl += 2;
     }
+    CK(viso_launch_grid(s->grid_jobs + 2 * t0, 2 * nf, s->grid, st));
+    ++nl;
+    /* descriptor rows are written in cell-sorted order, so they follow the grid */
+    if (any_f32 && max_n > 0) { CK(viso_launch_pack(s->pack_jobs + 2 * t0, 2 * nf, max_n, s->dlen, s->err, st)); ++nl; }
     if (any_img && max_n > 0) {
         CK(viso_launch_extract(s->extract_jobs + 2 * t0, 2 * nf, max_n, s->img_w, s->img_h, s->img_w, 5, st));
         ++nl;
     }
-    CK(viso_launch_grid(s->grid_jobs + 2 * t0, 2 * nf, s->grid, st));
-    ++nl;
     /* match jobs: frame 0 has one (stereo), frame t >= 1 has three (stereo, temporal L, temporal R) */
     const int mj0 = t0 == 0 ? 0 : 3 * t0 - 2, mj1 = 3 * t1 - 2;
     CK(cudaEventRecord(s->ev0, st));
     CK(viso_launch_match(s->match_jobs + mj0, mj1 - mj0, max_n, max_nt, mp, s->grid, s->pairs,
-                         PendingList{s->pending, s->pend_rec, s->pend_job, VISO_SEQ_PENDING_CAP}, st, &nl));
+                         PendingList{s->pending, s->pend_rec, s->pend_job, VISO_SEQ_PENDING_CAP}, ctx->match_mode,
+                         ctx->sm_count, st, &nl));
     CK(cudaEventRecord(s->ev1, st));
     CK(viso_launch_sort(s->sort_jobs + t0, nf, max_nL, pd, st));
     ++nl;
@@ -678,9 +680,19 @@ int viso_seq_get_packed(viso_seq* s, int t, int side, uint16_t* rows, int32_t* n
     if (rcc) return rcc;
     const int cnt = side ? s->h_nR[t] : s->h_nL[t];
     const uint16_t* src = (side ? s->dRu : s->dLu) + (size_t)t * s->cap * VISO_DESC_U16;
+    const int* pos = (side ? s->posR : s->posL) + (size_t)t * s->cap;
     *n = cnt;
-    if (cnt > 0) CK(cudaMemcpyAsync(rows, src, (size_t)cnt * VISO_DESC_U16 * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cnt <= 0) return VISO_OK;
+    /* the device keeps the rows in cell-sorted order; hand them back in the caller's keypoint order */
+    std::vector<uint16_t> sorted((size_t)cnt * VISO_DESC_U16);
+    std::vector<int> po(cnt);
+    CK(cudaMemcpyAsync(sorted.data(), src, sorted.size() * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(po.data(), pos, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < cnt; ++i) {
+        if (po[i] < 0 || po[i] >= cnt) return ctx->fail(VISO_ERR_CUDA, "seq_get_packed: corrupt position table");
+        std::memcpy(rows + (size_t)i * VISO_DESC_U16, sorted.data() + (size_t)po[i] * VISO_DESC_U16, VISO_DESC_U16 * 2);
+    }
     return VISO_OK;
 }
 

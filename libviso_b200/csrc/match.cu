@@ -11,8 +11,9 @@
 /* ------------------------------------------------------------------------------------------------ pack */
 
 /*
- * f32 cv::Mat descriptor rows (viso.cpp:999-1002) -> biased u16 rows (v + 1024, pad elements 0), plus the u32 sum
- * of the packed row.  One warp per row, lane l owns elements 4l..4l+3.  Also the domain check (integer valued,
+ * f32 cv::Mat descriptor rows (viso.cpp:999-1002) -> biased u16 rows (v + 1024, pad elements 0) in CELL-SORTED order
+ * (row p is the descriptor of keypoint srec[p].z), plus the u32 sum of the packed row into srec[p].w.  Runs after
+ * grid_build_kernel.  One warp per row, lane l owns elements 4l..4l+3.  Also the domain check (integer valued,
  * |v| <= 1023).
  */
 __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restrict__ jobs, int dlen, int* err)
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
     const int n = *job.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int row = blockIdx.x * 8 + warp; row < n; row += gridDim.x * 8) {
-        const float* src = job.d + (size_t)row * dlen;
+        const float* src = job.d + (size_t)job.srec[row].z * dlen;
         unsigned u[4];
         unsigned sum = 0;
         int bad = 0;
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
         w.y = u[2] | (u[3] << 16);
         reinterpret_cast<uint2*>(job.out + (size_t)row * VISO_DESC_U16)[lane] = w;
         const unsigned tot = warp_sum_u(sum);
-        if (lane == 0) job.rsum[row] = tot;
+        if (lane == 0) job.srec[row].w = tot;
         if (bad) atomicOr(err, 1);
     }
 }
@@ -62,7 +63,8 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
  * byte per window row; a row of the window is one contiguous run for the half warp), forms the vertical [1 2 1] sums
  * in registers, and the horizontal difference s(x+1) - s(x-1) comes from the lane two to the right by shuffle.
  * The 121 values go through a 256-byte shared-memory row to reach the packed layout (16 bytes per lane) and the row
- * sum.  The image is touched once per frame, so the loads mostly miss to DRAM: a warp issues the loads of
+ * sum.  In the pipeline the kernel runs after grid_build_kernel and walks the CELL-SORTED records: row p of the output
+ * is the descriptor at srec[p].xy and its sum lands in srec[p].w (job.srec == null: rows follow job.kp, sums to rsum).  The image is touched once per frame, so the loads mostly miss to DRAM: a warp issues the loads of
  * VISO_EXTRACT_ROUNDS x 2 keypoints before using any.
  */
 #ifndef VISO_EXTRACT_ROUNDS
@@ -97,7 +99,10 @@ __global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __r
         unsigned char p[VISO_EXTRACT_ROUNDS][wside];
 #pragma unroll
         for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
-            const float2 kp = job.kp[min(row0 + 2 * q + half, n - 1)];
+            const int kr = min(row0 + 2 * q + half, n - 1);
+            float2 kp;
+            if (job.srec) { const uint4 sr = job.srec[kr]; kp = make_float2(__uint_as_float(sr.x), __uint_as_float(sr.y)); }
+            else kp = job.kp[kr];
             px[q] = __float2int_rn(kp.x); py[q] = __float2int_rn(kp.y);
             /* the whole window inside the image: no reflection, no masked sample (uniform over the half warp) */
             interior[q] = px[q] > radius && px[q] + radius + 1 < width && py[q] > radius && py[q] + radius + 1 < height;
@@ -138,7 +143,10 @@ __global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __r
             for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o, 16);
             if (row < n) {
                 reinterpret_cast<uint4*>(job.out + (size_t)row * VISO_DESC_U16)[col] = w;
-                if (col == 0) job.rsum[row] = sum;
+                if (col == 0) {
+                    if (job.srec) job.srec[row].w = sum;
+                    else job.rsum[row] = sum;
+                }
             }
         }
         __syncwarp();
@@ -149,7 +157,8 @@ __global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __r
 
 /*
  * Counting sort of one keypoint set into 16-px cells (one CTA per set).  Emits, in cell order, the candidate
- * records the matcher streams: srec = (x, y, original index, row sum).
+ * records the matcher streams: srec = (x, y, original index, row sum -- filled in by the pack / extract kernel that
+ * follows), and the inverse permutation pos_of.
  */
 __global__ void __launch_bounds__(512) grid_build_kernel(const GridJob* __restrict__ jobs, GridCfg g)
 {
@@ -187,7 +196,8 @@ __global__ void __launch_bounds__(512) grid_build_kernel(const GridJob* __restri
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         float2 p = job.xy[i];
         int pos = atomicAdd(&cursor[cell_coord(p.y, g.gy) * g.gx + cell_coord(p.x, g.gx)], 1);
-        job.srec[pos] = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), (unsigned)i, job.rsum[i]);
+        job.srec[pos] = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), (unsigned)i, 0u);
+        job.pos_of[i] = pos;
     }
 }
 
@@ -314,13 +324,14 @@ struct GlobalVisitor {
             const bool in = fl < total;
             float dist = CUDART_INF_F;
             uint4 rec = make_uint4(0, 0, 0xffffffffu, 0);
+            int p = 0;
             if (in) {
                 while (fl >= ws.rowPre[row + 1]) ++row;
-                const int p = ws.rowS0[row] + (fl - ws.rowPre[row]);
+                p = ws.rowS0[row] + (fl - ws.rowPre[row]);
                 rec = __ldg(t.srec + p);
                 dist = l1_dist(q.qx, q.qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
             }
-            f(in, dist, rec);
+            f(in, dist, rec, p);
         }
     }
 
@@ -363,16 +374,17 @@ struct BestState {
  * entries past the end of the list are clamped to the last one (a repeated L1-hit load) and masked afterwards, so
  * that all 2*NS row loads of the batch can be in flight together. */
 /* where the candidates of a query come from: target index of entry e, and (index, L1 distance bits, row sum) */
-struct ListAcc { /* the warp's uint4 list (generic kernel) */
+struct ListAcc { /* the warp's uint4 list (generic kernel): (target index, L1 distance bits, row sum, sorted position) */
     const WarpScratch& ws;
-    __device__ __forceinline__ unsigned index(int e) const { return ws.list[e].x; }
     __device__ __forceinline__ uint4 entry(int e) const { return ws.list[e]; }
+    __device__ __forceinline__ unsigned pos(const uint4& ent) const { return ent.w; }
 };
 struct TileAcc { /* region indices into the staged neighbourhood (tile kernel): the distance is recomputed */
     const unsigned short* ql;
     const uint4* reg;
+    const int* pos_of;
     float qx, qy;
-    __device__ __forceinline__ unsigned index(int e) const { return reg[ql[e]].z; }
+    __device__ __forceinline__ unsigned pos(const uint4& ent) const { return (unsigned)__ldg(pos_of + ent.x); }
     __device__ __forceinline__ uint4 entry(int e) const
     {
         const uint4 r = reg[ql[e]];
@@ -390,6 +402,7 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
     const bool b0 = sub & 1, b1 = sub & 2, b2 = sub & 4;
     /* lane L fetches the record of candidate base + L once; the steps and the final fold get it by shuffle */
     const uint4 ent = acc_.entry(min(base + lane, n - 1));
+    const unsigned epos = acc_.pos(ent); /* sorted position = row of the candidate's descriptor */
     unsigned part[NB];
 #pragma unroll
     for (int s = 0; s < NB; ++s) part[s] = 0;
@@ -399,8 +412,8 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
 #pragma unroll
         for (int s = 0; s < VISO_EVAL_DEPTH; ++s) {
             if (h + s < NL) {
-                const unsigned idx = __shfl_sync(FULL, ent.x, 4 * (h + s) + g);
-                const uint4* rp = tbase + (size_t)idx * (VISO_DESC_U16 / 8);
+                const unsigned rowp = __shfl_sync(FULL, epos, 4 * (h + s) + g);
+                const uint4* rp = tbase + (size_t)rowp * (VISO_DESC_U16 / 8);
                 ra[s] = __ldg(rp);
                 rb[s] = __ldg(rp + 8);
             }
@@ -526,7 +539,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
     const int q = (int)qrec.z;
     const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
     const unsigned qsum = qrec.w;
-    const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7);
+    const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)__ldg(job.q.pos_of + q) * VISO_DESC_U16) + (lane & 7);
     const uint4 qa = __ldg(qp), qb = __ldg(qp + 8);
     const float r = P.radius;
     const int K = P.K;
@@ -549,7 +562,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
         for (int b = lane; b < VISO_HIST_BINS; b += 32) ws.sel.hist[b] = 0;
         __syncwarp();
         int cnt = 0;
-        vis.all([&](bool in, float dist, uint4 rec) {
+        vis.all([&](bool in, float dist, uint4 rec, int) {
             const bool inL = in && dist <= r && dist < D0;
             if (inL) atomicAdd(&ws.sel.hist[dist_bin(dist, bscale)], 1u);
             cnt += __popc(__ballot_sync(FULL, inL));
@@ -581,7 +594,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
             if (m < nb) {
                 if (nb <= VISO_TIE_CAP) {
                     int fill = 0;
-                    vis.all([&](bool in, float dist, uint4 rec) {
+                    vis.all([&](bool in, float dist, uint4 rec, int) {
                         const bool hitb = in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb;
                         const unsigned bm = __ballot_sync(FULL, hitb);
                         if (hitb) {
@@ -609,7 +622,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
                     float curD = -1.f; int curI = -1;
                     for (int it = 0; it < m; ++it) {
                         float bestD = CUDART_INF_F; int bestI = INT_MAX;
-                        vis.all([&](bool in, float dist, uint4 rec) {
+                        vis.all([&](bool in, float dist, uint4 rec, int) {
                             const int idx = (int)rec.z;
                             if (in && dist <= r && dist < D0 && dist_bin(dist, bscale) == tb &&
                                 key_greater(dist, idx, curD, curI) && key_greater(bestD, bestI, dist, idx)) {
@@ -634,7 +647,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
     /* final pass: membership, Sampson gate, append to the list (membership of a point does not depend on the
      * others once the threshold is known, so the list can be evaluated and reset at any time) */
     int nlist = 0;
-    vis.all([&](bool in, float dist, uint4 rec) {
+    vis.all([&](bool in, float dist, uint4 rec, int p) {
         const int idx = (int)rec.z;
         bool take = in && dist <= r && dist < D0;
         if (take && Tbin != INT_MAX) {
@@ -647,7 +660,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
         }
         const unsigned tm = __ballot_sync(FULL, take);
         if (tm == 0) return;
-        if (take) ws.list[nlist + __popc(tm & ((1u << lane) - 1))] = make_uint4(rec.z, __float_as_uint(dist), rec.w, 0u);
+        if (take) ws.list[nlist + __popc(tm & ((1u << lane) - 1))] = make_uint4(rec.z, __float_as_uint(dist), rec.w, (unsigned)p);
         nlist += __popc(tm);
         if (nlist > VISO_LIST_CAP - 32) {
             __syncwarp();
@@ -848,7 +861,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                 }
                 const int q = (int)qrec.z;
                 const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
-                const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)q * VISO_DESC_U16) + (lane & 7);
+                const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)__ldg(job.q.pos_of + q) * VISO_DESC_U16) + (lane & 7);
                 const uint4 qa = __ldg(qp), qb = __ldg(qp + 8);
                 BestState st;
                 st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
@@ -872,7 +885,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                     }
                     __syncwarp();
                 }
-                if (nlist > 0) eval_list(job.t.desc, TileAcc{ql, reg, qx, qy}, nlist, lane, qa, qb, qrec.w, st);
+                if (nlist > 0) eval_list(job.t.desc, TileAcc{ql, reg, job.t.pos_of, qx, qy}, nlist, lane, qa, qb, qrec.w, st);
                 pairs += nlist;
                 if (lane == 0) write_result(job, P, q, st);
             }
@@ -929,6 +942,337 @@ sad_match_generic_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, 
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ staged tile kernel */
+
+/* 1-D bulk async copies (TMA engine, SASS UBLKCP) completing on an mbarrier */
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+
+#define VISO_ST_WARPS 8
+#define VISO_ST_SLOTS 64          /* queries of a tile handled per round */
+#define VISO_ST_MAX_TH 8          /* tile height in cells at most */
+#define VISO_ST_MAX_ROWS 32       /* grid rows a staged neighbourhood may span (one lane of warp 0 each) */
+
+struct StagedCfg {
+    int tw, th;       /* query tile in cells */
+    int cap_rows;     /* staging capacity in descriptor rows / candidate records */
+    int ql_cap;       /* per-query candidate list capacity */
+};
+
+/*
+ * sad_match_staged_kernel: match_desc (viso.cpp:668-722) for a batch of jobs with the descriptor rows of a tile's
+ * neighbourhood STAGED IN SHARED MEMORY.  blockIdx.y = job, blockIdx.x = query tile (cfg.tw x cfg.th cells).
+ *
+ * Descriptor rows live in HBM in cell-sorted order, so the target points that can be within `radius` of any query of
+ * the tile are one contiguous span of rows (and of candidate records) per grid row.  Warp 0 works out those spans --
+ * the bounding box of the tile's query coordinates grown by radius + slack, each grid row trimmed to the reach that
+ * is left at its vertical distance -- and its lanes issue one cp.async.bulk per span for the 16-byte records and one
+ * for the 256-byte rows, each set completing on its own mbarrier.  No thread touches the data on its way in.
+ *
+ * 1. (records arrived) Candidate generation, LANE = QUERY: every warp walks a share of the staged records; the point is
+ *    a shared-memory broadcast and each lane tests it against its own query (radius and index-0 terminator, viso.cpp:
+ *    693), appending hits to that query's list.
+ * 2. (rows arrived) Evaluation, WARP = QUERY, LANE = CANDIDATE: each lane computes the complete 121-element SAD of its
+ *    own candidate against the query -- no cross-lane reduction.  The query row sits in registers, 16 chunks of 16
+ *    bytes; lane l walks the chunks in the order s ^ (l & 7), so the eight lanes of a quarter warp always read eight
+ *    different 16-byte bank groups whatever rows they are on (rows are 256 bytes apart: without the rotation all
+ *    lanes would hit the same four banks).  Per element pair one VIMNMX.U16x2 + one add: sum|a-b| = sum a + sum b -
+ *    2 sum min(a,b), packed u16 partial sums of 32 words never carry.  Each lane keeps its own (best, second best,
+ *    tie-break key); one REDUX fold per query at the end.  Ties on the SAD go to the largest (L1, index) key = the
+ *    last in the reference's scan order (viso.cpp:703).
+ * Queries that need the top-K cut or overflow their list, and tiles whose neighbourhood does not fit the staging
+ * buffers, are left to sad_match_generic_kernel through the pending list, exactly like the gather tile kernel.
+ */
+__global__ void __launch_bounds__(VISO_ST_WARPS * 32, 2)
+sad_match_staged_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, StagedCfg cfg,
+                        unsigned long long* sad_pairs, PendingList pend)
+{
+    extern __shared__ __align__(128) unsigned char st_smem[];
+    unsigned char* const rows = st_smem;                                                /* cap_rows x 256 B */
+    uint4* const reg = reinterpret_cast<uint4*>(st_smem + (size_t)cfg.cap_rows * 256);  /* cap_rows records */
+    unsigned short* const qlist = reinterpret_cast<unsigned short*>(reg + cfg.cap_rows);
+    const int ql_cap = cfg.ql_cap, ql_stride = ql_cap + 2; /* odd word stride: lanes = queries write conflict free */
+    __shared__ int qcnt[VISO_ST_SLOTS];
+    __shared__ uint4 qrec_s[VISO_ST_SLOTS];
+    __shared__ int qpos_s[VISO_ST_SLOTS];
+    __shared__ int tile_s[2];
+    __shared__ __align__(8) unsigned long long mbar[2];
+
+    const MatchJob job = jobs[blockIdx.y];
+    const MatchParamsDev& P = mp.p[job.mode];
+    const int nq = *job.q.n, nt = *job.t.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (g.gx + cfg.tw - 1) / cfg.tw;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    if (ty * cfg.th >= g.gy || nq <= 0) return;
+
+    /* the tile's queries: one span of the cell-sorted query array per cell row */
+    const int cx_lo = tx * cfg.tw, cx_hi = min(cx_lo + cfg.tw, g.gx);
+    int qtot = 0;
+    int qs[VISO_ST_MAX_TH], ql[VISO_ST_MAX_TH];
+#pragma unroll
+    for (int rr = 0; rr < VISO_ST_MAX_TH; ++rr) {
+        const int cy = ty * cfg.th + rr;
+        qs[rr] = 0; ql[rr] = 0;
+        if (rr < cfg.th && cy < g.gy) {
+            qs[rr] = __ldg(job.q.cell_start + cy * g.gx + cx_lo);
+            ql[rr] = __ldg(job.q.cell_start + cy * g.gx + cx_hi) - qs[rr];
+        }
+        qtot += ql[rr];
+    }
+    if (qtot == 0) return;
+
+    auto query_pos = [&](int k) {
+        int pos = 0;
+#pragma unroll
+        for (int rr = 0; rr < VISO_ST_MAX_TH; ++rr) {
+            if (k >= 0 && k < ql[rr]) pos = qs[rr] + k;
+            k -= ql[rr];
+        }
+        return pos;
+    };
+
+    if (nt <= 0) { /* no targets: every query is unmatched */
+        for (int k = threadIdx.x; k < qtot; k += blockDim.x)
+            job.out[__ldg(job.q.srec + query_pos(k)).z] = make_int4(-1, INT_MAX, INT_MAX, 0);
+        return;
+    }
+
+    const float r = P.radius;
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            mbar_fence_init();
+        }
+        /* bounding box of the tile's query coordinates (queries outside the image extent are clamped into border
+         * cells, so the cell rectangle is not a bound) */
+        float xmin = CUDART_INF_F, xmax = -CUDART_INF_F, ymin = CUDART_INF_F, ymax = -CUDART_INF_F, amax = 0.f;
+        for (int k = lane; k < qtot; k += 32) {
+            const uint4 qr = __ldg(job.q.srec + query_pos(k));
+            const float x = __uint_as_float(qr.x), y = __uint_as_float(qr.y);
+            xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+            amax = fmaxf(amax, fabsf(x) + fabsf(y));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = fminf(xmin, __shfl_xor_sync(FULL, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(FULL, xmax, o));
+            ymin = fminf(ymin, __shfl_xor_sync(FULL, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, o));
+            amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
+        }
+        /* reach: radius + the largest per-query slack (make_geom) + a margin far above the float rounding of the sums */
+        const float grow = r + (1.0f + 4e-6f * (amax + r)) + 4e-6f * (amax + r) + 1e-3f;
+        const int cy0 = cell_coord(ymin - grow, g.gy), cy1 = cell_coord(ymax + grow, g.gy);
+        const int nr = cy1 - cy0 + 1;
+        int total = -1; /* -1: no staging */
+        if (nr <= VISO_ST_MAX_ROWS && xmin == xmin && ymin == ymin) {
+            /* lane = grid row of the neighbourhood: the reach left at the row's vertical distance from the box */
+            int start = 0, len = 0;
+            if (lane < nr) {
+                const int cy = cy0 + lane;
+                const float lo = (cy == 0) ? -CUDART_INF_F : (float)(cy * VISO_GRID_CS);
+                const float hi = (cy == g.gy - 1) ? CUDART_INF_F : (float)((cy + 1) * VISO_GRID_CS);
+                const float dymin = fmaxf(0.f, fmaxf(lo - ymax, ymin - hi));
+                const float rem = grow - dymin;
+                if (rem >= 0.f) {
+                    const int cx0 = cell_coord(xmin - rem, g.gx), cx1 = cell_coord(xmax + rem, g.gx);
+                    start = __ldg(job.t.cell_start + cy * g.gx + cx0);
+                    len = __ldg(job.t.cell_start + cy * g.gx + cx1 + 1) - start;
+                }
+            }
+            const int incl = warp_incl_scan(len, lane);
+            const int run = __shfl_sync(FULL, incl, 31);
+            if (run <= cfg.cap_rows) {
+                total = run;
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&mbar[0], (unsigned)run * 16u);
+                    mbar_arrive_expect_tx(&mbar[1], (unsigned)run * 256u);
+                }
+                if (len > 0) {
+                    const int off = incl - len;
+                    bulk_g2s(reg + off, job.t.srec + start, (unsigned)len * 16u, &mbar[0]);
+                    bulk_g2s(rows + (size_t)off * 256, job.t.desc + (size_t)start * VISO_DESC_U16, (unsigned)len * 256u, &mbar[1]);
+                }
+            }
+        }
+        if (lane == 0) tile_s[0] = total;
+    }
+    __syncthreads();
+    const int R = tile_s[0];
+
+    unsigned pairs = 0;
+    if (R < 0) { /* leave the whole tile to the generic kernel */
+        for (int k = threadIdx.x; k < qtot; k += blockDim.x) {
+            const uint4 qr = __ldg(job.q.srec + query_pos(k));
+            job.out[qr.z] = make_int4(0, 0, 0, VISO_PENDING);
+            pend_push(pend, qr, blockIdx.y);
+        }
+        return;
+    }
+    const float2 t0 = __ldg(job.t.xy);
+    const unsigned rows_u32 = smem_u32(rows);
+    const int rot = lane & 7;
+    for (int g0 = 0; g0 < qtot; g0 += VISO_ST_SLOTS) {
+        const int nslot = min(VISO_ST_SLOTS, qtot - g0);
+        if (g0 > 0) __syncthreads(); /* the previous round's lists are consumed */
+        if (threadIdx.x < VISO_ST_SLOTS) qcnt[threadIdx.x] = 0;
+        __syncthreads();
+        if (g0 == 0) mbar_wait(&mbar[0], 0); /* candidate records have landed */
+        {
+            /* lane = query slot.  Up to 32 queries: all warps share slots 0..31; else warps 0-3 take slots 0..31 and
+             * warps 4-7 slots 32..63; a warp walks every stride-th staged point */
+            const bool two = nslot > 32;
+            const int half = two ? (warp >> 2) : 0, part = two ? (warp & 3) : warp, stride = two ? 4 : 8;
+            const int slot = half * 32 + lane;
+            const bool act = slot < nslot;
+            const int qpos = query_pos(g0 + (act ? slot : 0));
+            const uint4 qr = __ldg(job.q.srec + qpos);
+            if (part == 0 && act) { qrec_s[slot] = qr; qpos_s[slot] = qpos; }
+            const float qx = __uint_as_float(qr.x), qy = __uint_as_float(qr.y);
+            const float d0 = l1_dist(qx, qy, t0.x, t0.y);
+            /* candidates need dist <= r and dist < D0 (index-0 rule), D0 = d0 if d0 <= r: one strict comparison
+             * against lim = min(next float above r, D0); lanes without a query get lim = -inf */
+            const float r_up = r < CUDART_INF_F ? __uint_as_float(__float_as_uint(r) + 1u) : r;
+            const float lim = act ? ((d0 <= r) ? d0 : r_up) : -CUDART_INF_F;
+            const float2* pts = reinterpret_cast<const float2*>(reg);
+            unsigned short* mylist = qlist + slot * ql_stride;
+#pragma unroll 4
+            for (int i = part; i < R; i += stride) {
+                const float2 p = pts[2 * i]; /* (x, y) of the uint4 record: broadcast */
+                const float dist = l1_dist(qx, qy, p.x, p.y);
+                if (dist < lim) {
+                    const int j = atomicAdd(&qcnt[slot], 1);
+                    if (j < ql_cap) mylist[j] = (unsigned short)i;
+                }
+            }
+        }
+        __syncthreads();
+        if (g0 == 0) mbar_wait(&mbar[1], 0); /* descriptor rows have landed */
+        for (int kk = warp; kk < nslot; kk += VISO_ST_WARPS) {
+            const uint4 qrec = qrec_s[kk];
+            const int n = qcnt[kk];
+            if (n > ql_cap || n > P.K) { /* top-K cut or list overflow: left to the generic kernel */
+                if (lane == 0) {
+                    job.out[qrec.z] = make_int4(0, 0, 0, VISO_PENDING);
+                    pend_push(pend, qrec, blockIdx.y);
+                }
+                continue;
+            }
+            const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
+            unsigned short* qlst = qlist + kk * ql_stride;
+            int nlist = n;
+            if (P.epipolar) { /* Sampson gate (viso.cpp:695-701), lanes = candidates, compacting the list in place */
+                nlist = 0;
+                for (int base = 0; base < n; base += 32) {
+                    const int e = base + lane;
+                    bool take = e < n;
+                    const unsigned short ri = qlst[take ? e : 0];
+                    if (take) {
+                        const uint4 rec = reg[ri];
+                        const double sd = sampson_dev(P.F, qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
+                        if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
+                    }
+                    const unsigned tm = __ballot_sync(FULL, take);
+                    __syncwarp(); /* every lane has read its entry before the slots are reused */
+                    if (take) qlst[nlist + __popc(tm & ((1u << lane) - 1))] = ri;
+                    nlist += __popc(tm);
+                }
+                __syncwarp();
+            }
+            BestState st;
+            st.b1 = 0xffffffffu; st.b2 = 0xffffffffu; st.bdist = 0; st.bidx = -1;
+            if (nlist > 0) {
+                /* the query row in this lane's chunk order */
+                const uint4* qp = reinterpret_cast<const uint4*>(job.q.desc + (size_t)qpos_s[kk] * VISO_DESC_U16);
+                uint4 qv[16];
+#pragma unroll
+                for (int s = 0; s < 16; ++s) qv[s] = __ldg(qp + (s ^ rot));
+                unsigned lb1 = 0xffffffffu, lb2 = 0xffffffffu, lkd = 0;
+                int lki = -1;
+                for (int base = 0; base < nlist; base += 32) {
+                    const int e = base + lane;
+                    const bool act = e < nlist;
+                    const unsigned ri = qlst[act ? e : 0];
+                    const uint4 rec = reg[ri];
+                    const unsigned ra = rows_u32 + ri * 256u + (unsigned)rot * 16u;
+                    unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const unsigned ad = ra ^ ((unsigned)s << 4);
+                        uint4 ta, tb;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ta.x), "=r"(ta.y), "=r"(ta.z), "=r"(ta.w) : "r"(ad));
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+128];" : "=r"(tb.x), "=r"(tb.y), "=r"(tb.z), "=r"(tb.w) : "r"(ad));
+                        a0 += __vminu2(qv[s].x, ta.x) + __vminu2(qv[s].y, ta.y);
+                        a1 += __vminu2(qv[s].z, ta.z) + __vminu2(qv[s].w, ta.w);
+                        a2 += __vminu2(qv[s + 8].x, tb.x) + __vminu2(qv[s + 8].y, tb.y);
+                        a3 += __vminu2(qv[s + 8].z, tb.z) + __vminu2(qv[s + 8].w, tb.w);
+                    }
+                    /* every accumulator holds 16 words x 2 halves, each half <= 16 x 2047: no carry */
+                    const unsigned tot = (a0 & 0xffffu) + (a0 >> 16) + (a1 & 0xffffu) + (a1 >> 16) + (a2 & 0xffffu) + (a2 >> 16) +
+                                         (a3 & 0xffffu) + (a3 >> 16);
+                    if (act) {
+                        const unsigned sad = qrec.w + rec.w - 2u * tot;
+                        const unsigned dbits = __float_as_uint(l1_dist(qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y)));
+                        const int idx = (int)rec.z;
+                        if (sad < lb1) {
+                            lb2 = lb1; lb1 = sad; lkd = dbits; lki = idx;
+                        } else if (sad == lb1) {
+                            lb2 = lb1;
+                            if (dbits > lkd || (dbits == lkd && idx > lki)) { lkd = dbits; lki = idx; }
+                        } else if (sad < lb2) {
+                            lb2 = sad;
+                        }
+                    }
+                }
+                /* fold the lanes: smallest SAD, ties to the largest (L1, index) key; second smallest with multiplicity */
+                const unsigned m1 = __reduce_min_sync(FULL, lb1);
+                const unsigned ties = __ballot_sync(FULL, lb1 == m1);
+                unsigned m2 = m1;
+                if (__popc(ties) < 2) m2 = __reduce_min_sync(FULL, lb1 == m1 ? lb2 : lb1);
+                const unsigned kd = __reduce_max_sync(FULL, lb1 == m1 ? lkd : 0u);
+                const int ki = __reduce_max_sync(FULL, (lb1 == m1 && lkd == kd) ? lki : -1);
+                st.b1 = m1; st.b2 = m2; st.bdist = kd; st.bidx = ki;
+                pairs += nlist;
+            }
+            if (lane == 0) write_result(job, P, (int)qrec.z, st);
+        }
+    }
+    if (sad_pairs && lane == 0 && pairs) {
+        atomicAdd(sad_pairs, (unsigned long long)pairs);
+        atomicAdd(sad_pairs + 1, (unsigned long long)pairs);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ launchers */
 
 cudaError_t viso_launch_pack(const PackJob* jobs, int n_jobs, int max_n, int dlen, int* err_flag, cudaStream_t s)
@@ -972,49 +1316,95 @@ cudaError_t viso_launch_grid(const GridJob* jobs, int n_jobs, GridCfg g, cudaStr
     return cudaGetLastError();
 }
 
-cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
-                              GridCfg g, unsigned long long* sad_pairs, PendingList pend, cudaStream_t s, int* launches)
+/* tile shape and staging capacities of sad_match_staged_kernel for the densest target set of the launch; false when
+ * even the smallest tile's neighbourhood cannot be staged (dense sets, huge radii): the gather tile kernel runs then */
+static bool staged_config(int max_nt, float r, GridCfg g, StagedCfg* out, size_t* smem_out)
 {
-    if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
-    static int mode = -1;
-    if (mode < 0) {
-        const char* m = getenv("VISO_MATCH_MODE");
-        mode = (m && m[0] == 'g') ? 1 : 0;
-    }
-    /* the generic kernel loops over query chunks: about 16 CTAs per SM in total, never more than one per chunk */
-    const int gchunks = (max_nq + VISO_STRIP_QPC - 1) / VISO_STRIP_QPC;
-    const dim3 ggrid(std::min(gchunks, std::max(1, (148 * 16 + n_jobs - 1) / n_jobs)), n_jobs);
-    if (mode == 1) {
-        sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, pend, 0);
-        if (launches) *launches += 1;
-        return cudaGetLastError();
-    }
-    /* staging capacity for a tile's neighbourhood: 1.5 x the expected point count of the grown tile box at the
-     * densest target set + 64, within [128, 6144] records of 16 bytes (shared memory not used here is L1 for the
-     * descriptor rows: measured 6.89 -> 6.72 ms against 2 x) */
-    const float r = fmaxf(mp.p[0].radius, mp.p[1].radius);
+    if (!(r >= 0.f) || !(r < 1e6f)) return false;
     const double ext_x = (double)g.gx * VISO_GRID_CS, ext_y = (double)g.gy * VISO_GRID_CS;
-    const double bx = fmin(ext_x, VISO_TILE_W * VISO_GRID_CS + 2.0 * (r + 2) + 2 * VISO_GRID_CS);
-    const double by = fmin(ext_y, VISO_TILE_H * VISO_GRID_CS + 2.0 * (r + 2) + 2 * VISO_GRID_CS);
-    double expect = (double)max_nt * (bx * by) / (ext_x * ext_y);
-    if (!(expect >= 0)) expect = 0;
-    int cap = (int)fmin(6144.0, fmax(128.0, 1.5 * expect + 64.0));
-    cap = (cap + 63) & ~63;
+    const double dens = (double)max_nt / (ext_x * ext_y);
     /* per-query list capacity: 1.5 x the expected number of points in the L1 diamond (2 r^2) + 16, 64..256 */
     const double in_diamond = (double)max_nt * fmin(1.0, 2.0 * (double)r * r / (ext_x * ext_y));
     int ql_cap = (int)fmin(256.0, fmax(64.0, 1.5 * in_diamond + 16.0));
     ql_cap = (ql_cap + 31) & ~31;
-    const size_t smem = (size_t)cap * sizeof(uint4) + (size_t)32 * (ql_cap + 2) * sizeof(unsigned short);
-    if (smem > 48 * 1024) { /* per device, so set whenever it is needed (a process may drive several GPUs) */
-        cudaError_t e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    /* two CTAs per SM: 227 KB / 2 less the static shared memory and the 1 KB the system reserves per CTA */
+    const size_t budget = 111 * 1024;
+    const size_t lists = (size_t)VISO_ST_SLOTS * (ql_cap + 2) * sizeof(unsigned short);
+    if (lists + 64 * 272 > budget) return false;
+    int cap_rows = (int)((budget - lists) / 272) & ~7;
+    static const int shapes[][2] = {{8, 4}, {6, 4}, {6, 3}, {4, 4}, {4, 3}, {4, 2}, {3, 2}, {2, 2}, {2, 1}, {1, 1}};
+    for (const auto& sh : shapes) {
+        const double bx = fmin(ext_x, sh[0] * VISO_GRID_CS + 2.0 * (r + 2) + VISO_GRID_CS);
+        const double by = fmin(ext_y, sh[1] * VISO_GRID_CS + 2.0 * (r + 2) + VISO_GRID_CS);
+        if (by / VISO_GRID_CS + 1 > VISO_ST_MAX_ROWS) continue;
+        /* the four corners of the box are out of every query's reach and are not staged */
+        const double area = fmax(0.25 * bx * by, bx * by - 1.4 * fmin((double)r * r, 0.25 * bx * by));
+        if (1.3 * dens * area + 24.0 <= cap_rows) {
+            out->tw = sh[0]; out->th = sh[1]; out->cap_rows = cap_rows; out->ql_cap = ql_cap;
+            *smem_out = (size_t)cap_rows * 272 + lists;
+            return true;
+        }
     }
+    return false;
+}
+
+cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
+                              GridCfg g, unsigned long long* sad_pairs, PendingList pend, int mode, int sm_count,
+                              cudaStream_t s, int* launches)
+{
+    if (n_jobs <= 0 || max_nq <= 0) return cudaSuccess;
+    if (sm_count <= 0) sm_count = 148;
+    /* the generic kernel loops over query chunks: about 16 CTAs per SM in total, never more than one per chunk */
+    const int gchunks = (max_nq + VISO_STRIP_QPC - 1) / VISO_STRIP_QPC;
+    const dim3 ggrid(std::min(gchunks, std::max(1, (sm_count * 16 + n_jobs - 1) / n_jobs)), n_jobs);
+    if (mode == VISO_MATCH_GENERIC) {
+        sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, pend, 0);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
+    const float r = fmaxf(mp.p[0].radius, mp.p[1].radius);
     /* a kernel, not cudaMemsetAsync: memsets and copies on the compute stream can be scheduled on a copy engine and
      * then wait behind every upload queued there (see viso_seq_run_range) */
     cudaError_t e = viso_launch_zero(pend.count, 1, s);
     if (e != cudaSuccess) return e;
-    const int tiles = ((g.gx + VISO_TILE_W - 1) / VISO_TILE_W) * ((g.gy + VISO_TILE_H - 1) / VISO_TILE_H);
-    sad_match_kernel<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, ql_cap, sad_pairs, pend);
+    StagedCfg sc;
+    size_t st_smem = 0;
+    bool staged = mode != VISO_MATCH_GATHER && staged_config(max_nt, r, g, &sc, &st_smem);
+    if (!staged && mode == VISO_MATCH_STAGED) { /* forced: smallest tile, whatever does not fit goes to the generic kernel */
+        sc.tw = 1; sc.th = 1; sc.ql_cap = 256;
+        const size_t lists = (size_t)VISO_ST_SLOTS * (sc.ql_cap + 2) * sizeof(unsigned short);
+        sc.cap_rows = (int)((111 * 1024 - lists) / 272) & ~7;
+        st_smem = (size_t)sc.cap_rows * 272 + lists;
+        staged = true;
+    }
+    if (staged) {
+        e = cudaFuncSetAttribute(sad_match_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem);
+        if (e != cudaSuccess) return e;
+        const int tiles = ((g.gx + sc.tw - 1) / sc.tw) * ((g.gy + sc.th - 1) / sc.th);
+        sad_match_staged_kernel<<<dim3(tiles, n_jobs), VISO_ST_WARPS * 32, st_smem, s>>>(jobs, mp, g, sc, sad_pairs, pend);
+    } else {
+        /* staging capacity for a tile's neighbourhood: 1.5 x the expected point count of the grown tile box at the
+         * densest target set + 64, within [128, 6144] records of 16 bytes (shared memory not used here is L1 for the
+         * descriptor rows: measured 6.89 -> 6.72 ms against 2 x) */
+        const double ext_x = (double)g.gx * VISO_GRID_CS, ext_y = (double)g.gy * VISO_GRID_CS;
+        const double bx = fmin(ext_x, VISO_TILE_W * VISO_GRID_CS + 2.0 * (r + 2) + 2 * VISO_GRID_CS);
+        const double by = fmin(ext_y, VISO_TILE_H * VISO_GRID_CS + 2.0 * (r + 2) + 2 * VISO_GRID_CS);
+        double expect = (double)max_nt * (bx * by) / (ext_x * ext_y);
+        if (!(expect >= 0)) expect = 0;
+        int cap = (int)fmin(6144.0, fmax(128.0, 1.5 * expect + 64.0));
+        cap = (cap + 63) & ~63;
+        /* per-query list capacity: 1.5 x the expected number of points in the L1 diamond (2 r^2) + 16, 64..256 */
+        const double in_diamond = (double)max_nt * fmin(1.0, 2.0 * (double)r * r / (ext_x * ext_y));
+        int ql_cap = (int)fmin(256.0, fmax(64.0, 1.5 * in_diamond + 16.0));
+        ql_cap = (ql_cap + 31) & ~31;
+        const size_t smem = (size_t)cap * sizeof(uint4) + (size_t)32 * (ql_cap + 2) * sizeof(unsigned short);
+        if (smem > 48 * 1024) { /* per device, so set whenever it is needed (a process may drive several GPUs) */
+            e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        const int tiles = ((g.gx + VISO_TILE_W - 1) / VISO_TILE_W) * ((g.gy + VISO_TILE_H - 1) / VISO_TILE_H);
+        sad_match_kernel<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, ql_cap, sad_pairs, pend);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, pend, 1);

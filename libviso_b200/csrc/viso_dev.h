@@ -4,10 +4,12 @@
  * HBM layout (see DESIGN.md "Data layout"):
  *   keypoints        float2[n]                      original order (index = the reference's keypoint index)
  *   descriptors f32  float[n][desc_len]             the reference's cv::Mat layout (input only)
- *   descriptors u16  uint16[n][128]                 biased (v+1024) Sobel values, pad elements 0; 256 B per row
- *   row sums         uint32[n]                      sum of the biased row (SAD = sum a + sum b - 2 sum min(a,b))
- *   candidate grid   cell_start int[ncell+1], srec uint4[n] = (x, y, index, row sum)
- *                                                   counting sort by 16-px cell
+ *   descriptors u16  uint16[n][128]                 biased (v+1024) Sobel values, pad elements 0; 256 B per row;
+ *                                                   rows in CELL-SORTED order (row p belongs to srec[p]), so the
+ *                                                   neighbourhood of a query tile is one contiguous span per grid row
+ *   candidate grid   cell_start int[ncell+1], srec uint4[n] = (x, y, original index, row sum), pos_of int[n]
+ *                                                   counting sort by 16-px cell; row sum = sum of the biased row
+ *                                                   (SAD = sum a + sum b - 2 sum min(a,b)); pos_of[i] = sorted position
  *   dense match out  int4[n]                        (best_idx, best_d1, best_d2, valid) per query
  */
 #ifndef VISO_DEV_H_
@@ -45,9 +47,10 @@ struct GridCfg { int gx, gy; };
 struct SetView {
     const float2* xy;        /* original order */
     const int* n;            /* device pointer to the keypoint count */
-    const uint16_t* desc;    /* packed rows, original order */
+    const uint16_t* desc;    /* packed rows, CELL-SORTED order (row p <-> srec[p]) */
     const uint4* srec;       /* cell-sorted candidate records: (x, y, original index, row sum) */
     const int* cell_start;   /* ncell+1 */
+    const int* pos_of;       /* original index -> sorted position */
 };
 
 struct MatchParamsDev {
@@ -70,20 +73,21 @@ struct MatchJob {
 };
 
 struct PackJob {
-    const float* d;          /* n x dlen float */
+    const float* d;          /* n x dlen float, original order */
     const int* n;
-    uint16_t* out;           /* n x 128 u16 */
-    unsigned* rsum;          /* n row sums */
+    uint16_t* out;           /* n x 128 u16, cell-sorted order */
+    uint4* srec;             /* cell-sorted records: .z = source row, .w receives the row sum */
     const int* from_image;   /* != 0: this set's descriptors come from extract_desc_kernel, skip */
 };
 
 /* MyFeatureExtractor::computeImpl on the device (viso.cpp:1004-1024): 8-bit image -> packed descriptor rows */
 struct ExtractJob {
     const unsigned char* img; /* rows x pitch */
-    const float2* kp;
+    const float2* kp;         /* srec == null: keypoints, row k of `out` belongs to kp[k] */
     const int* n;
     uint16_t* out;            /* n x 128 u16 */
-    unsigned* rsum;
+    unsigned* rsum;           /* srec == null: row sums */
+    uint4* srec;              /* != null: cell-sorted records; row p is extracted at srec[p].xy, its sum goes to srec[p].w */
     const int* from_image;    /* == 0: skip (descriptors were uploaded as f32 rows) */
 };
 
@@ -109,8 +113,8 @@ struct HarrisCfg {
 struct GridJob {
     const float2* xy;
     const int* n;
-    const unsigned* rsum;
-    uint4* srec;
+    int* pos_of;             /* out: original index -> sorted position */
+    uint4* srec;             /* out: (x, y, original index, 0); the pack / extract kernels fill in .w */
     int* cell_start;
 };
 
@@ -191,8 +195,15 @@ struct PendingList {
     int* job;
     int cap;
 };
+/* mode: VISO_MATCH_AUTO picks the staged tile kernel when a tile's neighbourhood fits shared memory, else the
+ * gather tile kernel; the others force one path (tests, A/B measurements).  sm_count sizes the generic kernel's grid. */
+#define VISO_MATCH_AUTO 0
+#define VISO_MATCH_GENERIC 1
+#define VISO_MATCH_GATHER 2
+#define VISO_MATCH_STAGED 3
 cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int max_nt, const MatchParamsPair& mp,
-                              GridCfg g, unsigned long long* sad_pairs, PendingList pend, cudaStream_t s, int* launches);
+                              GridCfg g, unsigned long long* sad_pairs, PendingList pend, int mode, int sm_count,
+                              cudaStream_t s, int* launches);
 cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, int max_n, ParamDev p, cudaStream_t s);
 cudaError_t viso_launch_circle(const CircleJob* jobs, int n_jobs, cudaStream_t s);
 cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, int max_n, ParamDev p, cudaStream_t s,
