@@ -27,6 +27,10 @@
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <sstream>
+#include <limits>
+#include <map>
+#include <set>
 #include <memory>
 #include <stdexcept>
 #include <string>

@@ -926,8 +926,10 @@ void viso_F_from_P(const double P1[12], const double P2[12], int normalise, doub
             F[r * 3 + c] = host_det4(M);
         }
     if (normalise && F[8] > DBL_MIN) {
-        const double s = F[8];
-        for (int i = 0; i < 9; i++) F[i] /= s;
+        /* viso.cpp:1177-1180, `F /= F.at<double>(2,2)`: cv::Mat's operator/=(Mat&, double) is a.convertTo(a, -1, 1./s)
+         * (opencv2/core/mat.inl.hpp), i.e. a multiplication by the reciprocal, not a division */
+        const double inv = 1. / F[8];
+        for (int i = 0; i < 9; i++) F[i] = F[i] * inv;
     }
 }
 

@@ -382,13 +382,14 @@ struct ListAcc { /* the warp's uint4 list (generic kernel): (target index, L1 di
 struct TileAcc { /* region indices into the staged neighbourhood (tile kernel): the distance is recomputed */
     const unsigned short* ql;
     const uint4* reg;
-    const int* pos_of;
+    const int* regpos;   /* sorted position (= descriptor row) of every staged record */
     float qx, qy;
-    __device__ __forceinline__ unsigned pos(const uint4& ent) const { return (unsigned)__ldg(pos_of + ent.x); }
+    __device__ __forceinline__ unsigned pos(const uint4& ent) const { return ent.w; }
     __device__ __forceinline__ uint4 entry(int e) const
     {
-        const uint4 r = reg[ql[e]];
-        return make_uint4(r.z, __float_as_uint(l1_dist(qx, qy, __uint_as_float(r.x), __uint_as_float(r.y))), r.w, 0u);
+        const unsigned ri = ql[e];
+        const uint4 r = reg[ri];
+        return make_uint4(r.z, __float_as_uint(l1_dist(qx, qy, __uint_as_float(r.x), __uint_as_float(r.y))), r.w, (unsigned)regpos[ri]);
     }
 };
 
@@ -711,7 +712,8 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     extern __shared__ uint4 reg[];                                /* staged neighbourhood, reg_cap records */
     /* per-query candidate lists (region indices), 32 x (ql_cap + 2): the +2 makes the word stride odd so that
      * lanes = queries write without bank conflicts */
-    unsigned short* const qlist = reinterpret_cast<unsigned short*>(reg + reg_cap);
+    int* const regpos = reinterpret_cast<int*>(reg + reg_cap);    /* sorted position of every staged record */
+    unsigned short* const qlist = reinterpret_cast<unsigned short*>(regpos + reg_cap);
     const int ql_stride = ql_cap + 2;
     __shared__ int qcnt[32];
     __shared__ int row_off[VISO_MAX_REG_ROWS + 1];
@@ -815,8 +817,9 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
         const int R = tile_s[3];
         for (int rr = warp; rr < nrows; rr += VISO_MATCH_WARPS) {
             const int o = row_off[rr], len = row_off[rr + 1] - o;
-            const uint4* src = job.t.srec + __ldg(job.t.cell_start + (rcy0 + rr) * g.gx + rcx0);
-            for (int i = lane; i < len; i += 32) reg[o + i] = __ldg(src + i);
+            const int p0 = __ldg(job.t.cell_start + (rcy0 + rr) * g.gx + rcx0);
+            const uint4* src = job.t.srec + p0;
+            for (int i = lane; i < len; i += 32) { reg[o + i] = __ldg(src + i); regpos[o + i] = p0 + i; }
         }
         const float2 t0 = __ldg(job.t.xy);
         for (int g0 = 0; g0 < qtot; g0 += 32) { /* groups of 32 queries: lane = query */
@@ -885,7 +888,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                     }
                     __syncwarp();
                 }
-                if (nlist > 0) eval_list(job.t.desc, TileAcc{ql, reg, job.t.pos_of, qx, qy}, nlist, lane, qa, qb, qrec.w, st);
+                if (nlist > 0) eval_list(job.t.desc, TileAcc{ql, reg, regpos, qx, qy}, nlist, lane, qa, qb, qrec.w, st);
                 pairs += nlist;
                 if (lane == 0) write_result(job, P, q, st);
             }
@@ -1369,7 +1372,9 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
     if (e != cudaSuccess) return e;
     StagedCfg sc;
     size_t st_smem = 0;
-    bool staged = mode != VISO_MATCH_GATHER && staged_config(max_nt, r, g, &sc, &st_smem);
+    /* AUTO runs the gather tile kernel: the staged kernel measured slower on B200 (10.6 vs 7.0 ms per 1000-frame launch,
+     * DESIGN.md section 5); VISO_MATCH_STAGED selects it */
+    bool staged = mode == VISO_MATCH_STAGED && staged_config(max_nt, r, g, &sc, &st_smem);
     if (!staged && mode == VISO_MATCH_STAGED) { /* forced: smallest tile, whatever does not fit goes to the generic kernel */
         sc.tw = 1; sc.th = 1; sc.ql_cap = 256;
         const size_t lists = (size_t)VISO_ST_SLOTS * (sc.ql_cap + 2) * sizeof(unsigned short);
@@ -1397,7 +1402,7 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
         const double in_diamond = (double)max_nt * fmin(1.0, 2.0 * (double)r * r / (ext_x * ext_y));
         int ql_cap = (int)fmin(256.0, fmax(64.0, 1.5 * in_diamond + 16.0));
         ql_cap = (ql_cap + 31) & ~31;
-        const size_t smem = (size_t)cap * sizeof(uint4) + (size_t)32 * (ql_cap + 2) * sizeof(unsigned short);
+        const size_t smem = (size_t)cap * (sizeof(uint4) + sizeof(int)) + (size_t)32 * (ql_cap + 2) * sizeof(unsigned short);
         if (smem > 48 * 1024) { /* per device, so set whenever it is needed (a process may drive several GPUs) */
             e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;

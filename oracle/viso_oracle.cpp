@@ -598,9 +598,11 @@ void vo_F_from_P(const double P1[12], const double P2[12], int normalise, double
             }
             F[r * 3 + c] = vo_determinant(M, 4);
         }
-    if (normalise && F[8] > DBL_MIN) { /* viso.cpp:1177-1180 */
-        double s = F[8];
-        for (int i = 0; i < 9; i++) F[i] /= s;
+    if (normalise && F[8] > DBL_MIN) {
+        /* viso.cpp:1177-1180, `F /= F.at<double>(2,2)`: OpenCV's operator/=(Mat&, double) is a.convertTo(a, -1, 1./s)
+         * (opencv2/core/mat.inl.hpp) -- every element is MULTIPLIED by the reciprocal */
+        const double inv = 1. / F[8];
+        for (int i = 0; i < 9; i++) F[i] = F[i] * inv;
     }
 }
 
