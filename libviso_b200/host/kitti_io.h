@@ -7,7 +7,7 @@
 #ifndef VISO_B200_HOST_KITTI_IO_H_
 #define VISO_B200_HOST_KITTI_IO_H_
 
-#include "cvcompat.h"
+#include <opencv2/core/core.hpp>
 
 #include <cstdio>
 #include <string>

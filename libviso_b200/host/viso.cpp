@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cassert>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <random>
@@ -250,15 +251,6 @@ void tr2mat(vector<double> tr, Mat& Tr)
     viso_tr2mat(tr.data(), Tr.ptr<double>(0));
 }
 
-/* reference src/mvg.h:41-66 (T = double), without the normalisation of viso.cpp:1177-1180 */
-Mat F_from_P(const Mat& P1, const Mat& P2)
-{
-    assert(P1.rows == 3 && P1.cols == 4 && P2.rows == 3 && P2.cols == 4);
-    Mat F(3, 3, cv::DataType<double>::type);
-    viso_F_from_P(P1.ptr<double>(0), P2.ptr<double>(0), 0, F.ptr<double>(0));
-    return F;
-}
-
 /* reference src/mvg.cpp:124-169 */
 Mat triangulate_dlt(const Mat& x1, const Mat& x2, const Mat& P1, const Mat& P2)
 {
@@ -293,6 +285,61 @@ void solveRigidMotion(const Mat& A, const Mat& B, Mat& T)
     T.create(4, 4, cv::DataType<float>::type);
     ck(viso_solve_rigid_motion(ctx(), A.ptr<float>(0), B.ptr<float>(0), A.cols, T.ptr<float>(0)));
 }
+
+/* the reference's signature (src/estimation.h:7-9) */
+void solveRigidMotion(const Eigen::MatrixXf& A, const Eigen::MatrixXf& B, Eigen::Affine3f& T)
+{
+    assert(A.cols() > 1 && A.cols() == B.cols() && A.rows() == B.rows() && A.rows() == 3); /* estimation.cpp:32-39 */
+    const int n = (int)A.cols();
+    Mat a(3, n, CV_32FC1), b(3, n, CV_32FC1), t;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < n; ++c) { a.at<float>(r, c) = A(r, c); b.at<float>(r, c) = B(r, c); }
+    solveRigidMotion(a, b, t);
+    Eigen::Matrix3f R;
+    Eigen::Vector3f tv;
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R(r, c) = t.at<float>(r, c); tv(r) = t.at<float>(r, 3); }
+    T = R;                  /* estimation.cpp:49-50 */
+    T.translation() = tv;
+}
+
+/* reference src/viso.cpp:469-483: host bookkeeping (point copies) */
+void collect_matches(const KeyPoints& kp1, const KeyPoints& kp2, const Matches& match, Points2f& p1, Points2f& p2, int lim)
+{
+    p1.clear(); p2.clear();
+    int i = 0;
+    for (const Match& m : match) {
+        if (i >= lim) break;
+        p1.push_back(kp1.at(m[0]).pt);
+        p2.push_back(kp2.at(m[1]).pt);
+        ++i;
+    }
+}
+
+/* reference src/mvg.cpp:33-42 */
+vector<int> arange(int range)
+{
+    assert(range >= 0);
+    vector<int> v(range);
+    for (int i = 0; i < range; ++i) v[i] = i;
+    return v;
+}
+
+/* reference src/mvg.cpp:92-107: P = K [R t], a once-per-rig 3 x 4 product (float storage, t read as T) */
+template <class T> Mat P_from_KRt(const Mat& K, const Mat& R, const Mat& t)
+{
+    Mat P(3, 4, CV_32FC1);
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) P.at<float>(i, j) = R.at<float>(i, j);
+        P.at<float>(i, 3) = (float)t.at<T>(i);
+    }
+    return K * P;
+}
+template Mat P_from_KRt<float>(const Mat&, const Mat&, const Mat&);
+template Mat P_from_KRt<double>(const Mat&, const Mat&, const Mat&);
+
+/* reference src/misc.cpp:3-15 */
+bool isEqual(double x, double y) { return std::abs(x - y) <= 1e-6 * std::abs(x); }
+bool isEqual(float x, float y) { return std::abs(x - y) <= 1e-6f * std::abs(x); }
 
 /* the per-frame loop of reference src/viso.cpp:1167-1330, batched */
 vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, FeatureSequence& frames)
@@ -352,7 +399,13 @@ vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, FeatureSequence& fra
 /* ---- front end: detector, extractor, images -> poses ---- */
 
 namespace {
-int g_max_features = 1200;   /* viso.cpp:1172 */
+int initial_max_features()
+{
+    const char* e = std::getenv("VISO_MAX_FEATURES");
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : 1200;   /* MAX_FEATURE_NUM, viso.cpp:1172 */
+}
+int g_max_features = initial_max_features();
 
 const unsigned char* image8(const Mat& image)
 {
@@ -404,7 +457,7 @@ void MyFeatureExtractor::compute(const Mat& image, KeyPoints& kp, Mat& d) const
 {
     std::lock_guard<std::mutex> l(G().mu);
     const unsigned char* img = image8(image);
-    d = Mat((int)kp.size(), descriptorSize(), cv::DataType<float>::type, 0.0);   /* viso.cpp:1008 */
+    d = Mat((int)kp.size(), descriptorSize(), cv::DataType<float>::type, Scalar(0));   /* viso.cpp:1008 */
     if (kp.empty()) return;
     const vector<float> a = kp_array(kp);
     ck(viso_extract_descriptors(ctx(), img, image.cols, image.rows, image.cols, a.data(), (int)kp.size(), d.ptr<float>(0)));
@@ -459,4 +512,24 @@ vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, StereoImageSource& i
     }
     viso_seq_destroy(seq);
     return poses;
+}
+
+/* reference src/viso.h:138-139 / src/viso.cpp:1167-1330: the generator is drained (cv::imread per frame, exactly the
+ * reference's loop condition at :1205) and the whole sequence goes to the device in one submission.  dbg_dir only
+ * receives debug JPEGs in the reference (:1232-1310); nothing is written here. */
+vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, StereoImageGenerator& images, const boost::filesystem::path& dbg_dir)
+{
+    (void)dbg_dir;
+    struct Adapter : StereoImageSource {
+        StereoImageGenerator& gen;
+        explicit Adapter(StereoImageGenerator& g_) : gen(g_) {}
+        bool next(image_pair& out)
+        {
+            StereoImageGenerator::result_type r = gen();
+            if (!r) return false;
+            out = *r;
+            return true;
+        }
+    } src(images);
+    return sequence_odometry(p1, p2, src);
 }

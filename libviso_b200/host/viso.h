@@ -1,28 +1,27 @@
 /*
- * viso.h (B200) -- the reference's hot-path API (reference src/viso.h, plus the header-less hot-path functions of
- * src/viso.cpp that have external linkage) with the same names, argument meaning and error behaviour; the bodies in
- * viso.cpp call the C-ABI of include/viso_b200.h and nothing else.  A caller written against the reference
- * (test/test.cpp:152-168, the per-frame loop of sequence_odometry) compiles against this header unchanged for the
- * functions listed here.  There is no CPU fallback: without a CUDA device every call throws viso_b200_error.
+ * viso.h (B200) -- the reference's public header (reference src/viso.h) restated declaration for declaration, so that
+ * code written against the reference -- src/kitti.cpp, test/test.cpp -- builds against this library unchanged: same
+ * includes, same using-declarations and typedefs (callers rely on them), `struct param`, the two image generators,
+ * and every function the reference defines, with the reference's signatures.  The bodies (viso.cpp in this
+ * directory) are marshalling layers over the C-ABI of include/viso_b200.h; all arithmetic of the per-frame path runs
+ * in libviso_b200.so on the GPU.  There is no CPU fallback: without a CUDA device every call throws viso_b200_error.
  *
- *   reference                                              here
- *   struct param                       viso.h:58-72        identical
- *   struct MatchParams                 viso.cpp:48-75      identical
- *   match_desc                         viso.cpp:668-726    identical signature
- *   match_circle                       viso.cpp:206-243    identical signature
- *   collect_matches (Mat x)            viso.cpp:501-514    identical signature
- *   triangulate_rectified<double>      viso.cpp:1137-1162  identical signatures (T = double)
- *   get_inliers                        viso.cpp:1509-1537  identical signature
- *   minimize_reproj                    viso.h:77-79        identical signature
- *   ransac_minimize_reproj             viso.h:74-75        identical signature
- *   tr2mat                             viso.h:162          identical signature
- *   F_from_P<double>                   mvg.h:41-66         F_from_P(P1, P2)
- *   per-frame loop of sequence_odometry viso.cpp:1205-1327 sequence_odometry(P1, P2, FeatureSequence&)
- *   HarrisBinnedFeatureDetector        viso.cpp:911-979    same constructor, detect(image, kp)
- *   MyFeatureExtractor                 viso.cpp:981-1025   same constructor, compute(image, kp, d)
- *   sequence_odometry                  viso.h:138-139      sequence_odometry(P1, P2, StereoImageSource&): images in,
- *                                                          poses out; StereoImageGenerator's cv::imread (viso.h:81-101)
- *                                                          is replaced by any source of 8-bit image pairs
+ *   reference src/viso.h                         here
+ *   :29-56   using / typedefs                    identical
+ *   :58-72   struct param                        identical
+ *   :74-79   ransac_minimize_reproj, minimize_reproj            identical signatures
+ *   :81-119  StereoImageGenerator, MonoImageGenerator           same members, same behaviour (cv::imread per frame)
+ *   :138-139 sequence_odometry(P1, P2, StereoImageGenerator&, dbg_dir)   identical signature; dbg_dir is accepted
+ *            and unused (the debug JPEG dumps of viso.cpp:1232-1310 are not produced)
+ *   :145-147 collect_matches(..., Points2f&, Points2f&, lim)    identical signature
+ *   :162     tr2mat                                             identical signature
+ *   :124-136, :142-144, :149-160  readCameraParams, getFundamentalMat, findConstrainedCorrespondences,
+ *            match_l2_2nd_best, match_epip_constraint (declared, never defined by the reference), save2 (debug
+ *            drawing), calibratedSFM (mono pipeline): declared for source compatibility, not defined
+ *
+ * Below the reference's surface: the hot-path functions that have external linkage in the reference's viso.cpp but no
+ * declaration in its header (match_desc, match_circle, collect_matches(Mat), triangulate_rectified<T>, get_inliers,
+ * MatchParams), the two front-end classes, and the knobs of this implementation (namespace viso_b200).
  *
  * RANSAC sampling: the reference seeds a fresh std::mt19937 from std::random_device per hypothesis
  * (viso.cpp:93-95), which is not reproducible.  Here the triples come from one std::mt19937 stream through the
@@ -32,30 +31,62 @@
 #ifndef VISO_B200_HOST_VISO_H_
 #define VISO_B200_HOST_VISO_H_
 
-#include "cvcompat.h"
+/* without an installed OpenCV / Boost / Eigen, compile with -I<repo>/compat (header stand-ins) */
+#include <opencv2/core/core.hpp>
+#include <opencv2/imgproc/imgproc.hpp>
+#include <opencv2/calib3d/calib3d.hpp>
+#include <opencv2/features2d/features2d.hpp>
+#include <opencv2/highgui/highgui.hpp>
+#include <opencv2/highgui/highgui_c.h>
+#include <opencv2/imgproc/types_c.h>
 
 #include <climits>
 #include <cstdint>
+#include <iomanip>
+#include <iostream>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
 
-using cv::KeyPoint;
+#include <boost/format.hpp>
+#include <boost/filesystem.hpp>
+
+#include <Eigen/Dense>
+
+#include "mvg.h"
+#include "misc.h"
+
+using namespace std;
+using namespace boost;
+
 using cv::Mat;
+using cv::KeyPoint;
+using cv::Vec2i;
+using cv::FeatureDetector;
+using cv::DescriptorExtractor;
+using cv::Scalar;
+using cv::FileStorage;
+using cv::Vec6f;
+using cv::Point2i;
+using cv::waitKey;
+using cv::Size;
+using cv::Point;
 using cv::Point2f;
 using cv::Vec3i;
 using cv::Vec4i;
-using std::pair;
-using std::vector;
+using Eigen::MatrixXf;
+using Eigen::Affine3f;
 
 typedef vector<KeyPoint> KeyPoints;
 typedef Vec3i Match; // i1, i2, dist
 typedef vector<Match> Matches;
 typedef vector<Point2f> Points2f;
 typedef Mat Descriptors;
+typedef pair<Mat, Mat> image_pair;
 
-/* reference src/viso.h:58-72 */
+/* reference src/viso.h:58-72 (member order is part of the contract: callers and the library share the layout) */
 struct param
 {
     param() : ransac_iter(50), inlier_threshold(2), thresh(1e-4), save_debug(true) {}
@@ -71,6 +102,80 @@ struct param
         double cv;
     } calib;
 };
+
+/* reference src/viso.h:74-79 */
+bool ransac_minimize_reproj(const Mat& X, const Mat& observe, vector<double>& best_tr, vector<int>& best_inliers,
+                            const struct param& param);
+bool minimize_reproj(const Mat& X, const Mat& observe, vector<double>& tr, const struct param& param,
+                     const vector<int>& active);
+
+/* reference src/viso.h:81-101: yields the pairs `mask % index` for index = begin .. end, read with cv::imread as
+ * 8-bit gray; the first unreadable pair ends the sequence */
+class StereoImageGenerator
+{
+public:
+    typedef boost::optional<image_pair> result_type;
+    typedef pair<string, string> string_pair;
+    StereoImageGenerator(const string_pair& mask, int begin = 0, int end = INT_MAX) : m_index(begin), m_end(end), m_mask(mask) {}
+    result_type operator()()
+    {
+        if (m_index > m_end) return result_type();
+        const string left = str(boost::format(m_mask.first) % m_index), right = str(boost::format(m_mask.second) % m_index);
+        image_pair p(cv::imread(left, CV_LOAD_IMAGE_GRAYSCALE), cv::imread(right, CV_LOAD_IMAGE_GRAYSCALE));
+        ++m_index;
+        return (p.first.data && p.second.data) ? result_type(p) : result_type();
+    }
+
+private:
+    int m_index, m_end;
+    string_pair m_mask;
+};
+
+/* reference src/viso.h:103-119 */
+class MonoImageGenerator
+{
+public:
+    typedef boost::optional<Mat> result_type;
+    MonoImageGenerator(const string& mask, int begin = 0, int end = INT_MAX) : m_index(begin), m_end(end), m_mask(mask) {}
+    result_type operator()()
+    {
+        if (m_index > m_end) return result_type();
+        Mat image = cv::imread(str(boost::format(m_mask) % m_index), CV_LOAD_IMAGE_GRAYSCALE);
+        ++m_index;
+        return image.data ? result_type(image) : result_type();
+    }
+
+private:
+    int m_index, m_end;
+    string m_mask;
+};
+
+/* reference src/viso.h:124-136: declared there, defined nowhere in the reference */
+void readCameraParams(const string& intrinsics_name, const string& extrinsics_name, StereoCam& p);
+Mat getFundamentalMat(const Mat& R1, const Mat& t1, const Mat& R2, const Mat& t2, const Mat& cameraMatrix);
+void findConstrainedCorrespondences(const Mat& F, const KeyPoints& kp1, const KeyPoints& kp2, const Mat& d1, const Mat& d2,
+                                    Matches& matches, double eps, double ratio);
+
+/* reference src/viso.h:138-139, src/viso.cpp:1167-1330: detection, description, stereo + temporal matching, circle
+ * closure, triangulation and RANSAC / Gauss-Newton for every stereo pair the generator yields; returns the chained
+ * 4 x 4 CV_64F poses, identity first; a frame with fewer than 3 circular matches or a failed RANSAC appends nothing */
+vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, StereoImageGenerator& images, const boost::filesystem::path& dbg_dir);
+
+/* reference src/viso.h:142-160 */
+void match_l2_2nd_best(const Descriptors& d1, const Descriptors& d2, Matches& match, float ratio = 0.7);     /* never defined */
+void collect_matches(const KeyPoints& kp1, const KeyPoints& kp2, const Matches& match, Points2f& p1, Points2f& p2,
+                     int lim = INT_MAX);                                                                      /* viso.cpp:469-483 */
+void match_epip_constraint(const cv::Mat& F, const KeyPoints& kp1, const KeyPoints& kp2, const Descriptors& d1,
+                           const Descriptors& d2, Matches& match, double ratio, double samp_thresh, double alg_thresh); /* never defined */
+void save2(const cv::Mat& m1, const cv::Mat& m2, const KeyPoints& kp1, const KeyPoints& kp2, const Matches& match,
+           const string& file_name, int lim = 50);                                                            /* debug drawing: not built */
+void calibratedSFM(const Mat& K, MonoImageGenerator& images);                                                 /* mono pipeline: not built */
+
+void tr2mat(vector<double> tr, Mat& Tr); /* reference src/viso.h:162, src/viso.cpp:109-133 */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Hot-path functions of src/viso.cpp that the reference's header does not declare (same names and signatures)
+ * ------------------------------------------------------------------------------------------------------------------ */
 
 /* reference src/viso.cpp:48-75 */
 struct MatchParams
@@ -103,16 +208,16 @@ namespace viso_b200 {
 void set_device(int device);            /* before the first call; default 0 */
 void set_ransac_seed(uint32_t seed);    /* restarts the sample stream */
 void set_sample_table(const vector<int>& table /* ransac_iter x 3, consumed by the next ransac call */);
+void set_max_features(int n);           /* MAX_FEATURE_NUM of sequence_odometry; the reference hard-codes 1200 (viso.cpp:1172);
+                                           the environment variable VISO_MAX_FEATURES sets the initial value */
 long long kernel_launches();
 }
 
 void match_desc(const KeyPoints& kp1, const KeyPoints& kp2, const Descriptors& d1, const Descriptors& d2,
-                Matches& match, const MatchParams& sp = MatchParams());
-
+                Matches& match, const MatchParams& sp = MatchParams());                       /* viso.cpp:668-726 */
 void match_circle(const Matches& match_lr, const Matches& match_lr_prev, const Matches& match11,
-                  const Matches& match22, vector<Vec4i>& circ_match, Matches& match_pcl);
-
-void collect_matches(const KeyPoints& kp1, const KeyPoints& kp2, const Matches& match, Mat& x);
+                  const Matches& match22, vector<Vec4i>& circ_match, Matches& match_pcl);      /* viso.cpp:206-243 */
+void collect_matches(const KeyPoints& kp1, const KeyPoints& kp2, const Matches& match, Mat& x); /* viso.cpp:501-514 */
 
 /* viso.cpp:1137-1154 (only T = double is used by the pipeline, viso.cpp:1247) and the param overload :1155-1162 */
 template <typename T> Mat triangulate_rectified(const Mat& x, double f, double base, double c1u, double c1v);
@@ -123,19 +228,9 @@ template <typename T> Mat triangulate_rectified(const Mat& x, const struct param
 }
 
 pair<vector<int>, double> get_inliers(const Mat& X, const Mat& observe, vector<double>& tr,
-                                      const struct param& param);
+                                      const struct param& param);                              /* viso.cpp:1509-1537 */
 
-bool minimize_reproj(const Mat& X, const Mat& observe, vector<double>& tr, const struct param& param,
-                     const vector<int>& active);
-
-bool ransac_minimize_reproj(const Mat& X, const Mat& observe, vector<double>& best_tr, vector<int>& best_inliers,
-                            const struct param& param);
-
-void tr2mat(vector<double> tr, Mat& Tr);
-
-Mat F_from_P(const Mat& P1, const Mat& P2);
-
-/* reference src/viso.cpp:911-979.  detect() clears nothing (cv::FeatureDetector::detect does: kp is replaced). The
+/* reference src/viso.cpp:911-979, on the device.  detect() replaces kp (cv::FeatureDetector::detect clears it).  The
  * reference leaves m_k uninitialised (:915-919, :978); here the constructor argument is stored.  Keypoint order
  * inside a bin: ascending (|response|, x, y) (include/viso_b200.h, viso_detect_harris). */
 class HarrisBinnedFeatureDetector {
@@ -149,7 +244,7 @@ private:
     float m_k;
 };
 
-/* reference src/viso.cpp:981-1025: d = kp.size() x (2r+1)^2 CV_32F; only r = 5 (the pipeline's, viso.cpp:1174) */
+/* reference src/viso.cpp:981-1025, on the device: d = kp.size() x (2r+1)^2 CV_32F; only r = 5 (viso.cpp:1174) */
 class MyFeatureExtractor {
 public:
     explicit MyFeatureExtractor(int descriptor_radius);
@@ -160,23 +255,12 @@ private:
     int m_descriptor_radius;
 };
 
-typedef pair<Mat, Mat> image_pair;   /* reference src/viso.h: left, right (CV_8U, same size) */
-
-/* Source of stereo pairs: the analogue of StereoImageGenerator::operator() (viso.h:86-96) without cv::imread;
- * next() returns false when the sequence ends (the reference stops at the first unreadable pair). */
+/* Any source of 8-bit stereo pairs (frames already in memory, a camera): next() returns false when the sequence ends */
 class StereoImageSource {
 public:
     virtual ~StereoImageSource() {}
     virtual bool next(image_pair& out) = 0;
 };
-
-namespace viso_b200 {
-void set_max_features(int n);   /* MAX_FEATURE_NUM of sequence_odometry; the reference hard-codes 1200 (viso.cpp:1172) */
-}
-
-/* sequence_odometry (viso.h:138-139, viso.cpp:1167-1330) from images: Harris detection, descriptors, matching, circle
- * closure, triangulation and RANSAC/Gauss-Newton all on the device; only the images go up and 64 bytes per frame
- * pair come back.  Debug image dumps (dbg_dir) are not produced. */
 vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, StereoImageSource& images);
 
 /* One frame's front-end output (HarrisBinnedFeatureDetector + MyFeatureExtractor, viso.cpp:1226-1231). */
@@ -185,7 +269,6 @@ struct FrameFeatures {
     Descriptors d1, d2;   /* n x 121 CV_32F */
 };
 
-/* Source of per-frame features, the analogue of StereoImageGenerator (viso.h:81-101) after the front-end. */
 class FeatureSequence {
 public:
     virtual ~FeatureSequence() {}
@@ -193,9 +276,7 @@ public:
     virtual const FrameFeatures& frame(size_t t) = 0;
 };
 
-/* the per-frame loop of sequence_odometry (viso.cpp:1205-1327): returns the chained 4x4 poses, identity first; frames
- * with < 3 circular matches or a failed RANSAC append nothing (viso.cpp:1283-1288, 1322-1324).  All frames are
- * processed in ONE batched device submission (frame pairs are independent given the features). */
+/* the per-frame loop of sequence_odometry (viso.cpp:1205-1327) from precomputed features, ONE batched device submission */
 vector<Mat> sequence_odometry(const Mat& p1, const Mat& p2, FeatureSequence& frames);
 
 #endif

@@ -165,8 +165,8 @@ static void build_world(World& w, const Mat& P1, const Mat& P2, int n_frames, in
             const float u1 = (float)std::floor(f * X / Z + cu), v = (float)std::floor(f * Y / Z + cv);
             const float u2 = (float)std::floor(f * (X - base) / Z + cu);
             if (u1 < 6 || u1 > 1234 || u2 < 6 || u2 > 1234 || v < 6 || v > 369 || u1 - u2 < 1) continue;
-            ff.kp1.push_back(KeyPoint(u1, v));
-            ff.kp2.push_back(KeyPoint(u2, v));
+            ff.kp1.push_back(KeyPoint(u1, v, 11.f));
+            ff.kp2.push_back(KeyPoint(u2, v, 11.f));
             for (int k = 0; k < 121; ++k) {
                 float a = desc[(size_t)i * 121 + k] + (float)un(gen), b = desc[(size_t)i * 121 + k] + (float)un(gen);
                 dl.push_back(std::max(-1020.f, std::min(1020.f, a)));
@@ -194,10 +194,9 @@ static void test_frame_loop()
     build_world(w, P1, P2, 4, 900);
 
     // ---- the reference's per-frame sequence, function by function (viso.cpp:1240-1313), vs the oracle
-    Mat F = F_from_P(P1, P2);
-    if (F.at<double>(2, 2) > 2.2250738585072014e-308) { // viso.cpp:1177-1180
-        const double s = F.at<double>(2, 2);
-        for (int i = 0; i < 9; ++i) F.ptr<double>(0)[i] /= s;
+    Mat F = F_from_P<double>(P1, P2);
+    if (F.at<double>(2, 2) > 2.2250738585072014e-308) { // viso.cpp:1177-1180, the reference's own statement
+        F /= F.at<double>(2, 2);
     }
     double Fo[9];
     vo_F_from_P(P1.ptr<double>(0), P2.ptr<double>(0), 1, Fo);
