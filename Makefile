@@ -6,9 +6,9 @@ NVCC ?= nvcc
 CXX ?= g++
 CSRC := libviso_b200/csrc
 SRCS := $(CSRC)/detect.cu $(CSRC)/match.cu $(CSRC)/sort_circle.cu $(CSRC)/estimation.cu $(CSRC)/geometry.cu $(CSRC)/capi.cu $(CSRC)/capi_seq.cu
-HDRS := $(CSRC)/viso_dev.h $(CSRC)/common.cuh $(CSRC)/introsort.h $(CSRC)/capi_internal.h include/viso_b200.h
+HDRS := $(CSRC)/viso_dev.h $(CSRC)/common.cuh $(CSRC)/introsort.h $(CSRC)/capi_internal.h $(CSRC)/glibc_sincos.h $(CSRC)/glibc_sincostab.inc include/viso_b200.h
 # -fmad=false: the FP64 estimation kernels evaluate the reference's expressions with separate multiplies and adds
-NVCCFLAGS ?= -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -O3 -std=c++17 -Xcompiler -fPIC -shared
+NVCCFLAGS ?= -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -O3 -std=c++17 -Xcompiler -fPIC,-fno-builtin-sin,-fno-builtin-cos -shared
 
 all: libviso_b200/libviso_b200.so
 

@@ -221,6 +221,10 @@ int viso_seq_upload_chunk_images(viso_seq* seq, int t0, int count, const uint8_t
  *   viso_seq_get_keypoints: the keypoints of frame t, side 0 (left) / 1 (right), after a run. */
 int viso_detect_harris(viso_ctx* ctx, const uint8_t* img, int width, int height, int pitch, int n_features, int nbinx,
                        int nbiny, float k, float* kp_xy, float* kp_response, int32_t* n_out);
+/* Test hook: sin(x[i]), cos(x[i]) as the estimation kernels evaluate them (glibc's algorithm, libviso_b200/csrc/
+ * glibc_sincos.h): bit-identical to the host libm for |x| < 105414350. */
+int viso_debug_sincos(viso_ctx* ctx, const double* x, int n, double* s, double* c);
+
 /* MyFeatureExtractor::computeImpl for one image (reference src/viso.cpp:1004-1024, descriptor radius 5): desc = n x 121
  * float, the reference's cv::Mat layout.  (Inside a sequence object the descriptors stay on the device in the packed
  * layout; this entry point exists for callers that use the extractor on its own.) */

@@ -327,6 +327,13 @@ class Context:
         return dict(ok=bool(ok.value), tr=tr, inliers=inl[:ni.value].copy(), hyp_tr=htr[:H], hyp_ok=hok[:H],
                     hyp_count=hc[:H], best_hyp=bh.value)
 
+    def debug_sincos(self, x):
+        """sin / cos as the estimation kernels evaluate them (glibc's algorithm on the device)"""
+        x = _f64(x).reshape(-1)
+        s = np.empty_like(x); c = np.empty_like(x)
+        self._ck(lib().viso_debug_sincos(self.h, _p(x), len(x), _p(s), _p(c)))
+        return s, c
+
     def sequence(self, n_frames, max_kp, desc_len=121, max_ransac_iter=50):
         return Sequence(self, n_frames, max_kp, desc_len, max_ransac_iter)
 

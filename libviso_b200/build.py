@@ -14,10 +14,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libviso_b200.so")
 SOURCES = ["detect.cu", "match.cu", "sort_circle.cu", "estimation.cu", "geometry.cu", "capi.cu", "capi_seq.cu"]
-HEADERS = [os.path.join(CSRC, "viso_dev.h"), os.path.join(CSRC, "introsort.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "capi_internal.h"),
+HEADERS = [os.path.join(CSRC, "viso_dev.h"), os.path.join(CSRC, "introsort.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "capi_internal.h"), os.path.join(CSRC, "glibc_sincos.h"), os.path.join(CSRC, "glibc_sincostab.inc"),
            os.path.join(os.path.dirname(HERE), "include", "viso_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC,-fno-builtin-sin,-fno-builtin-cos", "-shared"]
 
 
 def nvcc_path():

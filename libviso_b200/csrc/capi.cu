@@ -798,6 +798,9 @@ int viso_ransac_minimize_reproj(viso_ctx* ctx, const double* X, const double* ob
     if (n_inliers) *n_inliers = 0;
     if (best_hyp) *best_hyp = -1;
     if (n < 3) return VISO_OK; /* the reference's sampler cannot draw 3 of fewer than 3; report failure */
+    /* no hypotheses: the loop of viso.cpp:1555 never runs, best_inliers stays empty, :1571 returns false with best_tr
+     * untouched */
+    if (param->ransac_iter == 0) return VISO_OK;
     if (!X || !observe) return ctx->fail(VISO_ERR_ARG, "ransac_minimize_reproj: null input");
     const int H = param->ransac_iter;
     for (int i = 0; i < 3 * H; ++i)
@@ -844,6 +847,7 @@ int viso_ransac_minimize_reproj(viso_ctx* ctx, const double* X, const double* ob
     if (hyp_ok && H > 0) CK(cudaMemcpyAsync(hyp_ok, b.hyp_ok, (size_t)H * 4, cudaMemcpyDeviceToHost, s));
     if (hyp_count && H > 0) CK(cudaMemcpyAsync(hyp_count, b.hyp_count, (size_t)H * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (rec.n_inliers < 0 || rec.n_inliers > n) return ctx->fail(VISO_ERR_CUDA, "ransac_minimize_reproj: corrupt result record");
     if (inliers && rec.n_inliers > 0) {
         CK(cudaMemcpyAsync(inliers, b.inliers, (size_t)rec.n_inliers * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -1012,6 +1016,25 @@ int viso_detect_harris(viso_ctx* ctx, const uint8_t* img, int width, int height,
         CK(cudaStreamSynchronize(s));
     }
     *n_out = n;
+    return VISO_OK;
+}
+
+int viso_debug_sincos(viso_ctx* ctx, const double* x, int n, double* s, double* c)
+{
+    if (!ctx) return VISO_ERR_ARG;
+    if (n < 0 || (n > 0 && (!x || !s || !c))) return ctx->fail(VISO_ERR_ARG, "debug_sincos: bad argument");
+    if (n == 0) return VISO_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_scratch(ctx, (size_t)n * 24 + 256);
+    if (rc) return rc;
+    double* dx = reinterpret_cast<double*>(ctx->d_scr);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(viso_launch_sincos_probe(dx, n, dx + n, dx + 2 * (size_t)n, st));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(s, dx + n, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c, dx + 2 * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return VISO_OK;
 }
 

@@ -4,11 +4,14 @@
  *
  * Built with -fmad=false: the FP64 code must evaluate exactly the reference's expressions (separate multiply and
  * add, as a stock x86-64 build of the reference does) so that Jacobians, normal equations, LU pivots and inlier
- * decisions agree bit for bit with the CPU path.  Device sin / cos are the only operations that can differ from
- * glibc in the last place.
+ * decisions agree bit for bit with the CPU path.  sin / cos follow glibc's libm operation for operation
+ * (glibc_sincos.h), so the rotation entries are the CPU's as well.
  */
 #include "viso_dev.h"
 #include "common.cuh"
+#include "glibc_sincos.h"
+
+#include <algorithm>
 
 /* ------------------------------------------------------------------------------------------------ estimation */
 
@@ -25,8 +28,8 @@ __device__ __forceinline__ void make_rot(const double* tr, Rot& R, bool derivs)
 {
     const double rx = tr[0], ry = tr[1], rz = tr[2];
     R.tx = tr[3]; R.ty = tr[4]; R.tz = tr[5];
-    const double sx = sin(rx), cx = cos(rx), sy = sin(ry);
-    const double cy = cos(ry), sz = sin(rz), cz = cos(rz);
+    const double sx = viso_sc::sin_glibc(rx), cx = viso_sc::cos_glibc(rx), sy = viso_sc::sin_glibc(ry);
+    const double cy = viso_sc::cos_glibc(ry), sz = viso_sc::sin_glibc(rz), cz = viso_sc::cos_glibc(rz);
     R.r00 = +cy * cz;                R.r01 = -cy * sz;                R.r02 = +sy;
     R.r10 = +sx * sy * cz + cx * sz; R.r11 = -sx * sy * sz + cx * cz; R.r12 = -sx * cy;
     R.r20 = -cx * sy * cz + sx * sz; R.r21 = +cx * sy * sz + sx * cz; R.r22 = +cx * cy;
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4, VISO_HYP_MINB) ransac_hy
         for (int it = 0; it < 100; ++it) {
             /* make_rot, viso.cpp:1406-1424: lane 0 -> rx, lane 1 -> ry, lane 2 -> rz */
             const double ang = tr[q < 3 ? q : 0];
-            const double sv = sin(ang), cv = cos(ang);
+            const double sv = viso_sc::sin_glibc(ang), cv = viso_sc::cos_glibc(ang);
             Rot R;
             {
                 const double sx = __shfl_sync(qmask, sv, q0), cx = __shfl_sync(qmask, cv, q0);
@@ -557,5 +560,21 @@ cudaError_t viso_launch_inliers(const double* X, const double* obs, int n, int s
                                 int* count, ParamDev p, cudaStream_t s)
 {
     inliers_kernel<<<1, 256, 0, s>>>(X, obs, n, stride, tr, inliers, count, p);
+    return cudaGetLastError();
+}
+
+/* test hook: the device sin / cos of glibc_sincos.h over an array (tests/test_gpu_parity.py compares with the host libm) */
+__global__ void sincos_probe_kernel(const double* __restrict__ x, int n, double* __restrict__ s, double* __restrict__ c)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        s[i] = viso_sc::sin_glibc(x[i]);
+        c[i] = viso_sc::cos_glibc(x[i]);
+    }
+}
+
+cudaError_t viso_launch_sincos_probe(const double* x, int n, double* s, double* c, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    sincos_probe_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, st>>>(x, n, s, c);
     return cudaGetLastError();
 }

@@ -224,6 +224,7 @@ cudaError_t viso_launch_circle_generic(const int* lr, int nlr, const int* lrp, i
 cudaError_t viso_launch_collect_tri(const float2* kp1, int n1, const float2* kp2, int n2, const int* matches, int m,
                                     double* x, double* X, ParamDev p, int* err_flag, cudaStream_t s);
 
+cudaError_t viso_launch_sincos_probe(const double* x, int n, double* s, double* c, cudaStream_t st);
 cudaError_t viso_launch_triangulate_dlt(const float* x1, const float* x2, int m, const double* P1, const double* P2, float* X,
                                         cudaStream_t s);
 cudaError_t viso_launch_rigid_motion(const float* A, const float* B, int n, float* T, cudaStream_t s);

@@ -326,7 +326,20 @@ def test_get_inliers_and_minimize_reproj(ctx, api, oracle):
     assert_tr_close(tr_g, tr_o)
 
 
-@pytest.mark.parametrize("n,H", [(400, 50), (10000, 256)])
+def test_device_sincos_is_glibc_bit_for_bit(ctx, tmp_path):
+    """libviso_b200/csrc/glibc_sincos.h on the device against the host libm (what the oracle and the reference call,
+    viso.cpp:1410-1411): identical bits over every range below glibc's huge-argument reduction"""
+    from test_sincos import build_replica, libm_sincos, sincos_arguments
+    x = sincos_arguments(seed=1, n=300000)
+    x = np.ascontiguousarray(x[np.abs(x) < 105414350.0])
+    s, c = ctx.debug_sincos(x)
+    s0, c0 = libm_sincos(build_replica(tmp_path), x)
+    assert np.array_equal(s.view(np.int64), s0.view(np.int64))
+    assert np.array_equal(c.view(np.int64), c0.view(np.int64))
+    assert len(x) > 2_000_000
+
+
+@pytest.mark.parametrize("n,H", [(400, 50), (10000, 256), (10000, 4096)])   # the last one is BASELINE configs[3]
 def test_ransac_minimize_reproj(ctx, api, oracle, n, H):
     from libviso_b200 import synth
     X, obs, tr_true = synth.make_ransac_problem(n, seed=3000 + n)
@@ -338,11 +351,21 @@ def test_ransac_minimize_reproj(ctx, api, oracle, n, H):
     assert np.array_equal(g["hyp_ok"], o["hyp_ok"])
     assert np.array_equal(g["hyp_count"], o["hyp_count"])
     okm = o["hyp_ok"] == 1
-    assert_tr_close(g["hyp_tr"][okm], o["hyp_tr"][okm])
+    assert np.array_equal(g["hyp_tr"][okm], o["hyp_tr"][okm])   # same arithmetic, same libm: the hypotheses are identical
     assert g["best_hyp"] == o["best_hyp"]
     assert np.array_equal(g["inliers"], o["inliers"])
     assert_tr_close(g["tr"], o["tr"])
     assert np.abs(g["tr"] - tr_true).max() < 0.05
+
+
+def test_ransac_zero_iterations(ctx, api, oracle):
+    """param.ransac_iter == 0: the loop of viso.cpp:1555 never runs -> false, best_tr untouched, no inliers"""
+    from libviso_b200 import synth
+    X, obs, _ = synth.make_ransac_problem(50, seed=1)
+    pg, _ = _params(api, oracle, 0)
+    tr0 = np.array([0.1, 0.2, 0.3, 1, 2, 3.0])
+    g = ctx.ransac_minimize_reproj(X, obs, pg, np.zeros((0, 3), np.int32), tr0)
+    assert not g["ok"] and np.array_equal(g["tr"], tr0) and len(g["inliers"]) == 0 and g["best_hyp"] == -1
 
 
 def test_ransac_failure_modes(ctx, api, oracle):
