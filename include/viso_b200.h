@@ -181,7 +181,12 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
 void viso_seq_destroy(viso_seq* seq);
 /* F, base, f, cu, cv from P1,P2 exactly as viso.cpp:1176-1187 */
 int viso_seq_set_calib(viso_seq* seq, const double P1[12], const double P2[12]);
-/* host -> device copy of one frame's features (through pinned staging, asynchronous on the context stream) */
+/* host -> device copy of one frame's features.  All viso_seq_upload_* functions enqueue cudaMemcpyAsync straight from
+ * the caller's buffers on the context's COPY stream and return at once: with pinned buffers the copy is truly
+ * asynchronous, so the source (this includes the seeds of viso_seq_set_seeds) must stay valid and unmodified until
+ * viso_sync(), viso_seq_download() or a later synchronisation point; pageable buffers are staged by the driver before
+ * the call returns.  The f32 descriptor staging on the device (2 x n_frames x max_kp x desc_len floats) is allocated
+ * by the first call of this function; image-mode sequences never pay for it. */
 int viso_seq_upload_frame(viso_seq* seq, int t, const float* kpL, int nL, const float* kpR, int nR,
                           const float* dL, const float* dR);
 /* Front-end on the device: MyFeatureExtractor::computeImpl, reference src/viso.cpp:1004-1024 (cv::Sobel x 3x3,
@@ -198,6 +203,12 @@ int viso_seq_upload_frame_images(viso_seq* seq, int t, const uint8_t* imgL, cons
 int viso_seq_capacity(const viso_seq* seq);
 int viso_seq_upload_chunk_images(viso_seq* seq, int t0, int count, const uint8_t* images, const float* kpL,
                                  const int32_t* nL, const float* kpR, const int32_t* nR);
+/* Device address of the F 64-byte result records (viso_record layout; record t is valid once the kernels of a run
+ * that covered frame t have finished on viso_stream(ctx)).  For consumers that stay on the GPU -- e.g. an NCCL gather
+ * of the records of several ranks -- without a round trip through host memory. */
+void* viso_seq_records_device(viso_seq* seq);
+/* device memory held by the sequence object, bytes */
+int64_t viso_seq_device_bytes(const viso_seq* seq);
 /* Detector on the device: HarrisBinnedFeatureDetector::detectImpl, reference src/viso.cpp:911-979
  * (cv::cornerHarris(block 3, aperture 5, k, BORDER_DEFAULT); nbinx x nbiny bins of (width/nbinx) x (height/nbiny)
  * pixels; per bin the n_features/(nbinx*nbiny) largest |response| != 0; bins concatenated binx outer, biny inner).
@@ -222,7 +233,7 @@ int viso_seq_upload_chunk_images(viso_seq* seq, int t0, int count, const uint8_t
 int viso_detect_harris(viso_ctx* ctx, const uint8_t* img, int width, int height, int pitch, int n_features, int nbinx,
                        int nbiny, float k, float* kp_xy, float* kp_response, int32_t* n_out);
 /* Test hook: sin(x[i]), cos(x[i]) as the estimation kernels evaluate them (glibc's algorithm, libviso_b200/csrc/
- * glibc_sincos.h): bit-identical to the host libm for |x| < 105414350. */
+ * glibc_sincos.h): bit-identical to the host libm for |x| < 0x1.921fbp+26 = 105414336. */
 int viso_debug_sincos(viso_ctx* ctx, const double* x, int n, double* s, double* c);
 
 /* MyFeatureExtractor::computeImpl for one image (reference src/viso.cpp:1004-1024, descriptor radius 5): desc = n x 121
@@ -237,6 +248,8 @@ int viso_seq_get_keypoints(viso_seq* seq, int t, int side, float* kp_xy, int32_t
 /* Uploads run on a dedicated copy stream.  viso_seq_run_range() orders itself after every upload enqueued so far and
  * enqueues the pipeline for frames [t0, t1) (frame pairs (t-1, t) for t in [max(t0,1), t1); frame t0-1 must have been
  * run before), so uploading chunk k+1 from pinned memory overlaps the kernels of chunk k. */
+/* Frames are processed in order: t0 may not exceed the number of frames already run since they were last uploaded
+ * (frame pair t0 reads frame t0 - 1's matches and 3-D points from the previous submission); VISO_ERR_ARG otherwise. */
 int viso_seq_run_range(viso_seq* seq, const viso_param* param, int t0, int t1);
 /* enqueue the whole pipeline for frames [0, n_frames).  seeds: host [n_frames][ransac_iter][3] uint32 (copied). */
 int viso_seq_run(viso_seq* seq, const viso_param* param, const uint32_t* seeds);

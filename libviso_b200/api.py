@@ -63,6 +63,10 @@ def lib():
         _lib.viso_destroy.argtypes = [C.c_void_p]
         _lib.viso_seq_destroy.restype = None
         _lib.viso_seq_destroy.argtypes = [C.c_void_p]
+        _lib.viso_seq_records_device.restype = C.c_void_p
+        _lib.viso_seq_records_device.argtypes = [C.c_void_p]
+        _lib.viso_seq_device_bytes.restype = C.c_int64
+        _lib.viso_seq_device_bytes.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -182,6 +186,10 @@ class Context:
 
     def sync(self):
         self._ck(lib().viso_sync(self.h))
+
+    def stream_ptr(self):
+        """the cudaStream_t every kernel of this context is launched on"""
+        return int(lib().viso_stream(self.h) or 0)
 
     def set_image_extent(self, w, h):
         self._ck(lib().viso_set_image_extent(self.h, int(w), int(h)))
@@ -392,6 +400,13 @@ class Sequence:
 
     def capacity(self):
         return int(lib().viso_seq_capacity(self.h))
+
+    def records_device_ptr(self):
+        """device address of the n_frames 64-byte records (for consumers that stay on the GPU, e.g. an NCCL gather)"""
+        return int(lib().viso_seq_records_device(self.h))
+
+    def device_bytes(self):
+        return int(lib().viso_seq_device_bytes(self.h))
 
     def upload_chunk_images_raw(self, t0, count, images_ptr, kpL_ptr, nL_ptr, kpR_ptr, nR_ptr):
         """count frames in three copies from (pinned) host blocks: images [count][2][H][W] u8, kp [count][capacity()][2] f32"""

@@ -55,7 +55,8 @@ struct viso_seq {
     HarrisCfg hc{};
     bool det_set = false;
     int det_n = 0;                        /* keypoints per image at most: per * nbins */
-    cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_compute = nullptr, ev_counts = nullptr;
+    int counts_hi = 0;                    /* frames [0, counts_hi): their host-side counts may still be read by an enqueued copy */
     int run_hi = 0;                       /* frames [0, run_hi) may still be read by enqueued kernels */
     int run_hi_total = 0;                 /* frames [0, run_hi_total) have been through the pipeline at least once */
     std::vector<RansacProb> h_probs;
@@ -64,6 +65,7 @@ struct viso_seq {
     bool have_ms = false, calib_set = false, ran = false;
     double Fm[9]{}, base = 0, f = 0, cu = 0, cv = 0;
     std::vector<void*> allocs;
+    size_t bytes = 0;                     /* device memory held by this object */
 };
 
 namespace {
@@ -74,6 +76,7 @@ template <class T> cudaError_t seq_alloc(viso_seq* s, T** p, size_t n)
     cudaError_t e = cudaMalloc(&v, std::max<size_t>(n, 1) * sizeof(T));
     if (e != cudaSuccess) return e;
     s->allocs.push_back(v);
+    s->bytes += std::max<size_t>(n, 1) * sizeof(T);
     *p = reinterpret_cast<T*>(v);
     return cudaSuccess;
 }
@@ -85,6 +88,7 @@ void seq_free(viso_seq* s)
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
     if (s->ev_compute) cudaEventDestroy(s->ev_compute);
+    if (s->ev_counts) cudaEventDestroy(s->ev_counts);
     if (s->h_nL) cudaFreeHost(s->h_nL);
     delete s;
 }
@@ -116,7 +120,6 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     } while (0)
     SA(kpL, F * cap); SA(kpR, F * cap); SA(srecL, F * cap); SA(srecR, F * cap);
     SA(posL, F * cap); SA(posR, F * cap);
-    SA(dLf, F * cap * desc_len); SA(dRf, F * cap * desc_len);
     SA(dLu, F * cap * VISO_DESC_U16); SA(dRu, F * cap * VISO_DESC_U16);
     SA(nL, F); SA(nR, F); SA(cellL, F * nc); SA(cellR, F * nc);
     SA(dense_lr, F * cap); SA(dense_11, F * cap); SA(dense_22, F * cap);
@@ -144,6 +147,7 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     if ((e = cudaEventCreate(&s->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&s->ev_compute, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&s->ev_counts, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMemsetAsync(s->from_image, 0, F * 4, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
     if ((e = cudaMemsetAsync(s->nL, 0, F * 4, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
     if ((e = cudaMemsetAsync(s->nR, 0, F * 4, st)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
@@ -169,9 +173,11 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
                        s->cellR + t * nc, s->posR + t * cap};
     };
     for (size_t t = 0; t < F; ++t) {
-        pj[2 * t] = PackJob{s->dLf + t * cap * desc_len, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->srecL + t * cap,
+        /* the f32 descriptor staging (2 x F x cap x desc_len floats: 2 GB for a 1000-frame sequence) is only allocated when
+         * descriptors are uploaded as cv::Mat rows (viso_seq_upload_frame); d is filled in then */
+        pj[2 * t] = PackJob{nullptr, s->nL + t, s->dLu + t * cap * VISO_DESC_U16, s->srecL + t * cap,
                             s->from_image + t};
-        pj[2 * t + 1] = PackJob{s->dRf + t * cap * desc_len, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->srecR + t * cap,
+        pj[2 * t + 1] = PackJob{nullptr, s->nR + t, s->dRu + t * cap * VISO_DESC_U16, s->srecR + t * cap,
                                 s->from_image + t};
         gj[2 * t] = GridJob{s->kpL + t * cap, s->nL + t, s->posL + t * cap, s->srecL + t * cap, s->cellL + t * nc};
         gj[2 * t + 1] = GridJob{s->kpR + t * cap, s->nR + t, s->posR + t * cap, s->srecR + t * cap, s->cellR + t * nc};
@@ -237,13 +243,43 @@ int viso_seq_set_calib(viso_seq* s, const double P1[12], const double P2[12])
 
 /* an upload that overwrites a frame enqueued kernels may still read has to wait for them (not for the others: that
  * is what lets the uploads of one chunk overlap the kernels of the previous one) */
-static int upload_guard(viso_seq* s, int t)
+static int upload_guard(viso_seq* s, int t, bool frame_data = true)
 {
     viso_ctx* ctx = s->ctx;
+    if (t < s->counts_hi) {
+        /* the per-frame counts live in pinned host words that run_range copies asynchronously: the copy reads them
+         * when it executes, so they may not be overwritten before it has */
+        CK(cudaEventSynchronize(s->ev_counts));
+        s->counts_hi = 0;
+    }
     if (t < s->run_hi) {
         CK(cudaStreamWaitEvent(ctx->copy_stream, s->ev_compute, 0));
         s->run_hi = 0; /* everything enqueued so far is now ordered before later uploads */
     }
+    if (frame_data && t < s->run_hi_total) s->run_hi_total = t; /* frames from t on have to be run again before a later range may start */
+    return VISO_OK;
+}
+
+/* first f32-descriptor upload: allocate the staging arrays and point the pack jobs at them */
+static int ensure_f32_staging(viso_seq* s)
+{
+    viso_ctx* ctx = s->ctx;
+    if (s->dLf) return VISO_OK;
+    const size_t F = s->F, cap = s->cap, dl = s->dlen;
+    cudaError_t e;
+    if ((e = seq_alloc(s, &s->dLf, F * cap * dl)) != cudaSuccess || (e = seq_alloc(s, &s->dRf, F * cap * dl)) != cudaSuccess) {
+        s->dLf = nullptr;
+        ctx->err = std::string("seq_upload_frame cudaMalloc: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? VISO_ERR_NOMEM : VISO_ERR_CUDA;
+    }
+    std::vector<PackJob> pj(2 * F);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(pj.data(), s->pack_jobs, pj.size() * sizeof(PackJob), cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < F; ++t) {
+        pj[2 * t].d = s->dLf + t * cap * dl;
+        pj[2 * t + 1].d = s->dRf + t * cap * dl;
+    }
+    CK(cudaMemcpy(s->pack_jobs, pj.data(), pj.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
     return VISO_OK;
 }
 
@@ -255,7 +291,9 @@ int viso_seq_upload_frame(viso_seq* s, int t, const float* kpL, int nL, const fl
     if (t < 0 || t >= s->F || nL < 0 || nR < 0 || nL > s->cap || nR > s->cap) return ctx->fail(VISO_ERR_ARG, "seq_upload_frame: bad frame index or keypoint count");
     if ((nL > 0 && (!kpL || !dL)) || (nR > 0 && (!kpR || !dR))) return ctx->fail(VISO_ERR_ARG, "seq_upload_frame: null input");
     CK(cudaSetDevice(ctx->device));
-    int rc = upload_guard(s, t);
+    int rc = ensure_f32_staging(s);
+    if (rc) return rc;
+    rc = upload_guard(s, t);
     if (rc) return rc;
     cudaStream_t st = ctx->copy_stream;
     const size_t cap = s->cap, dl = s->dlen;
@@ -332,6 +370,10 @@ int viso_seq_upload_frame_images(viso_seq* s, int t, const uint8_t* imgL, const 
 }
 
 int viso_seq_capacity(const viso_seq* s) { return s ? s->cap : 0; }
+
+void* viso_seq_records_device(viso_seq* s) { return s ? (void*)s->rec : nullptr; }
+
+int64_t viso_seq_device_bytes(const viso_seq* s) { return s ? (int64_t)s->bytes : 0; }
 
 int viso_seq_upload_chunk_images(viso_seq* s, int t0, int count, const uint8_t* images, const float* kpL, const int32_t* nL,
                                  const float* kpR, const int32_t* nR)
@@ -449,7 +491,7 @@ int viso_seq_set_seeds(viso_seq* s, const uint32_t* seeds, int ransac_iter)
     viso_ctx* ctx = s->ctx;
     if (ransac_iter < 0 || ransac_iter > s->maxH || (ransac_iter > 0 && !seeds)) return ctx->fail(VISO_ERR_ARG, "seq_set_seeds: bad argument");
     CK(cudaSetDevice(ctx->device));
-    int rc = upload_guard(s, 0);
+    int rc = upload_guard(s, 0, false);
     if (rc) return rc;
     cudaStream_t st = ctx->copy_stream;
     const size_t H = ransac_iter;
@@ -475,6 +517,8 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
     if (t0 < 0 || t1 > s->F || t0 >= t1) return ctx->fail(VISO_ERR_ARG, "seq_run_range: bad frame range");
     if (!s->calib_set) return ctx->fail(VISO_ERR_ARG, "seq_run: viso_seq_set_calib has not been called");
     if (s->H_cur != param->ransac_iter) return ctx->fail(VISO_ERR_ARG, "seq_run: seeds were set for a different ransac_iter");
+    if (t0 > s->run_hi_total)
+        return ctx->fail(VISO_ERR_ARG, "seq_run_range: frames before t0 have not been run since they were uploaded (ranges must be submitted in order)");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int nf = t1 - t0;
@@ -483,13 +527,15 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
      * sequence objects (measured: it serialises double-buffered pipelines completely).  Kernels of an earlier
      * submission may still read these words, hence the guard. */
     {
-        int rc = upload_guard(s, t0);
+        int rc = upload_guard(s, t0, false);
         if (rc) return rc;
         cudaStream_t cs = ctx->copy_stream;
         CK(cudaMemcpyAsync(s->nL + t0, s->h_nL + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, cs));
         CK(cudaMemcpyAsync(s->nR + t0, s->h_nR + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, cs));
         CK(cudaMemcpyAsync(s->from_image + t0, s->h_from_image + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, cs));
         if (s->det_set) CK(cudaMemcpyAsync(s->detect + t0, s->h_detect + t0, (size_t)nf * 4, cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(s->ev_counts, cs));
+        s->counts_hi = std::max(s->counts_hi, t1);
     }
     /* everything uploaded so far (frames, seeds, counts) is visible to the kernels below */
     CK(cudaEventRecord(s->ev_copy, ctx->copy_stream));

@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(256) ransac_score_kernel(const RansacProb* __r
     if (lane == 0) pb.hyp_count[hId] = cnt;
 }
 
+#define VISO_GN_PARALLEL_MIN 1024 /* active sets above this size use the parallel normal-equation sums */
 #define VISO_GN_STAGE 512 /* Jacobian rows staged in shared memory per round of the sequential sums (28 KB) */
 
 /*
@@ -355,37 +356,79 @@ __device__ int gn_block(const double* __restrict__ X, const double* __restrict__
         for (int j = 0; j < 6; ++j) tr[j] = tr_s[j];
         Rot R;
         make_rot(tr, R, true);
-        for (int i = threadIdx.x; i < na; i += blockDim.x) {
-            const int a = active[i];
-            double ob[4], rows[4][7];
+        if (na > VISO_GN_PARALLEL_MIN) {
+            /* Large active sets (BASELINE configs[3]: ~7000 inliers of 10 000): the 27 sums are formed in parallel --
+             * every thread accumulates the products of its own points (i = tid, tid + 256, ...), then a fixed
+             * shuffle tree per warp and the warps in order.  Deterministic, but not cv::mulTransposed's row order:
+             * the refined tr agrees with the sequential path to ~1e-13 relative (north_star's tolerance is 1e-6). */
+            double acc[27];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) ob[r] = obs[r * stride + a];
-            const double w = weight_of(P, obs[i]); /* column i, viso.cpp:1449 */
-            point_rows(R, P, X[a], X[stride + a], X[2 * stride + a], w, ob, rows);
+            for (int t = 0; t < 27; ++t) acc[t] = 0;
+            for (int i = threadIdx.x; i < na; i += blockDim.x) {
+                const int a = active[i];
+                double ob[4], rows[4][7];
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+                for (int r = 0; r < 4; ++r) ob[r] = obs[r * stride + a];
+                const double w = weight_of(P, obs[i]); /* column i, viso.cpp:1449 */
+                point_rows(R, P, X[a], X[stride + a], X[2 * stride + a], w, ob, rows);
 #pragma unroll
-                for (int c = 0; c < 7; ++c) scratch[(size_t)(4 * i + r) * 7 + c] = rows[r][c];
-        }
-        __syncthreads();
-        {
-            /* the rows come back through shared memory, VISO_GN_STAGE rows at a time (coalesced, all threads), so the
-             * 27 sequential accumulation chains read with shared-memory latency instead of L2 latency; the order of
-             * the additions is unchanged: chunks in order, rows ascending inside a chunk */
-            const int a = threadIdx.x < 27 ? c_pair_a[threadIdx.x] : 0, b = threadIdx.x < 27 ? c_pair_b[threadIdx.x] : 0;
-            double s = 0;
-            const int rowsN = 4 * na;
-            for (int k0 = 0; k0 < rowsN; k0 += VISO_GN_STAGE) {
-                const int cnt = min(VISO_GN_STAGE, rowsN - k0);
-                for (int e = threadIdx.x; e < cnt * 7; e += blockDim.x) stage_s[e] = scratch[(size_t)k0 * 7 + e];
-                __syncthreads();
-                if (threadIdx.x < 27) {
-#pragma unroll 8
-                    for (int k = 0; k < cnt; ++k) s += stage_s[k * 7 + a] * stage_s[k * 7 + b];
+                for (int r = 0; r < 4; ++r) {
+                    int t = 0;
+#pragma unroll
+                    for (int ja = 0; ja < 6; ++ja)
+#pragma unroll
+                        for (int jc = ja; jc < 6; ++jc) { acc[t] += rows[r][ja] * rows[r][jc]; ++t; }
+#pragma unroll
+                    for (int ja = 0; ja < 6; ++ja) acc[21 + ja] += rows[r][ja] * rows[r][6];
                 }
-                __syncthreads();
             }
-            if (threadIdx.x < 27) sums_s[threadIdx.x] = s;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+            for (int t = 0; t < 27; ++t) {
+                double v = acc[t];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                if (lane == 0) stage_s[warp * 27 + t] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x < 27) {
+                double sum = 0;
+                for (int w2 = 0; w2 < nw; ++w2) sum += stage_s[w2 * 27 + threadIdx.x];
+                sums_s[threadIdx.x] = sum;
+            }
+        } else {
+            for (int i = threadIdx.x; i < na; i += blockDim.x) {
+                const int a = active[i];
+                double ob[4], rows[4][7];
+    #pragma unroll
+                for (int r = 0; r < 4; ++r) ob[r] = obs[r * stride + a];
+                const double w = weight_of(P, obs[i]); /* column i, viso.cpp:1449 */
+                point_rows(R, P, X[a], X[stride + a], X[2 * stride + a], w, ob, rows);
+    #pragma unroll
+                for (int r = 0; r < 4; ++r)
+    #pragma unroll
+                    for (int c = 0; c < 7; ++c) scratch[(size_t)(4 * i + r) * 7 + c] = rows[r][c];
+            }
+            __syncthreads();
+            {
+                /* the rows come back through shared memory, VISO_GN_STAGE rows at a time (coalesced, all threads), so the
+                 * 27 sequential accumulation chains read with shared-memory latency instead of L2 latency; the order of
+                 * the additions is unchanged: chunks in order, rows ascending inside a chunk */
+                const int a = threadIdx.x < 27 ? c_pair_a[threadIdx.x] : 0, b = threadIdx.x < 27 ? c_pair_b[threadIdx.x] : 0;
+                double s = 0;
+                const int rowsN = 4 * na;
+                for (int k0 = 0; k0 < rowsN; k0 += VISO_GN_STAGE) {
+                    const int cnt = min(VISO_GN_STAGE, rowsN - k0);
+                    for (int e = threadIdx.x; e < cnt * 7; e += blockDim.x) stage_s[e] = scratch[(size_t)k0 * 7 + e];
+                    __syncthreads();
+                    if (threadIdx.x < 27) {
+    #pragma unroll 8
+                        for (int k = 0; k < cnt; ++k) s += stage_s[k * 7 + a] * stage_s[k * 7 + b];
+                    }
+                    __syncthreads();
+                }
+                if (threadIdx.x < 27) sums_s[threadIdx.x] = s;
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {

@@ -15,7 +15,7 @@
  * explicitly below with fma() / separate roundings -- the translation unit is compiled with -fmad=false, so nothing
  * else gets contracted.  The interpolation table is glibc's own (glibc_sincostab.inc, tools/gen_sincostab.py).
  *
- * Range: |x| < 105414350 (0x419921FB) follows glibc exactly: tiny, Taylor (|x| < 0.126), table (|x| < 0.855469),
+ * Range: high word of |x| below 0x419921FB (|x| < 0x1.921fbp+26 = 105414336) follows glibc exactly: tiny, Taylor (|x| < 0.126), table (|x| < 0.855469),
  * pi/2 - |x| (|x| < 2.426265) and the three-constant Cody-Waite reduction (reduce_sincos).  Larger arguments
  * (glibc: __branred) and non-finite ones take CUDA's sin / cos; the estimation never gets there with finite data
  * (the largest angle seen over 4096 hypotheses x 10000 outlier-ridden correspondences is 1.6e6).

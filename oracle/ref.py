@@ -182,6 +182,29 @@ def sequence_odometry(P1, P2, mask0, mask1, begin, end, seeds_one_frame, max_pos
     return poses[:n].copy()
 
 
+RECORD_DTYPE = np.dtype([("tr", np.float64, 6), ("ok", np.int32), ("n_inliers", np.int32), ("n_circ", np.int32), ("best_hyp", np.int32)])
+
+
+def pipeline(frames, P1, P2, ransac_iter, seeds):
+    """the per-frame loop of the reference's sequence_odometry on given features (list of dict(kpL, kpR, dL, dR)):
+    returns dict(records [n_frames] (best_hyp is not reported by the reference: -1), poses [n, 4, 4])"""
+    nF = len(frames)
+    nL = np.array([len(f["kpL"]) for f in frames], np.int32); nR = np.array([len(f["kpR"]) for f in frames], np.int32)
+    offL = np.zeros(nF, np.int64); offR = np.zeros(nF, np.int64)
+    offL[1:] = np.cumsum(nL)[:-1]; offR[1:] = np.cumsum(nR)[:-1]
+    kpL = _f32(np.concatenate([f["kpL"] for f in frames])); kpR = _f32(np.concatenate([f["kpR"] for f in frames]))
+    dL = _f32(np.concatenate([f["dL"] for f in frames])); dR = _f32(np.concatenate([f["dR"] for f in frames]))
+    P1c, P2c = _f64(P1).reshape(12), _f64(P2).reshape(12)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    assert seeds.shape == (nF, ransac_iter, 3)
+    rec = np.zeros(nF, RECORD_DTYPE)
+    poses = np.zeros((nF + 1, 4, 4)); npz = C.c_int32(0)
+    rc = lib().vr_pipeline(nF, _p(nL), _p(nR), _p(offL), _p(offR), _p(kpL), _p(kpR), _p(dL), _p(dR), dL.shape[1], _p(P1c), _p(P2c),
+                           int(ransac_iter), _p(seeds), _p(rec), _p(poses), C.byref(npz))
+    assert rc == 0
+    return dict(records=rec, poses=poses[:npz.value].copy())
+
+
 def triangulate_dlt(x1, x2, P1, P2):
     x1, x2 = _f32(x1), _f32(x2)
     m = x1.shape[1]

@@ -331,7 +331,7 @@ def test_device_sincos_is_glibc_bit_for_bit(ctx, tmp_path):
     viso.cpp:1410-1411): identical bits over every range below glibc's huge-argument reduction"""
     from test_sincos import build_replica, libm_sincos, sincos_arguments
     x = sincos_arguments(seed=1, n=300000)
-    x = np.ascontiguousarray(x[np.abs(x) < 105414350.0])
+    x = np.ascontiguousarray(x[np.abs(x) < float.fromhex("0x1.921fbp+26")])   # glibc's test is on the high word: k < 0x419921FB
     s, c = ctx.debug_sincos(x)
     s0, c0 = libm_sincos(build_replica(tmp_path), x)
     assert np.array_equal(s.view(np.int64), s0.view(np.int64))

@@ -284,6 +284,34 @@ def test_sequence_odometry_from_image_files(oracle, ref, small_sequence, tmp_pat
     assert np.abs(poses - o["poses"]).max() < 1e-9
 
 
+def test_pipeline_on_the_config1_sequence(oracle, ref, small_sequence):
+    """BASELINE configs[0]-style sequence (synthetic KITTI-shaped frames, given features, 50 hypotheses per frame pair):
+    the reference's own functions in the reference's loop order (ref_abi.inc vr_pipeline) against the oracle's
+    vo_sequence -- per frame pair the same ok / n_inliers / n_circ, tr and chained poses"""
+    from libviso_b200 import synth
+    frames, _ = small_sequence
+    P1, P2 = synth.kitti_calib()
+    H = 50
+    seeds = make_seeds(len(frames), H)
+    o = oracle.sequence(frames, P1, P2, oracle.param_default(ransac_iter=H), seeds)
+    r = ref.pipeline(frames, P1, P2, H, seeds)
+    for k in ("ok", "n_inliers", "n_circ"):
+        assert np.array_equal(o["records"][k], r["records"][k]), k
+    assert o["records"]["ok"][1:].all() and (o["records"]["n_circ"][1:] > 50).all()
+    assert np.array_equal(o["records"]["tr"], r["records"]["tr"])
+    assert len(o["poses"]) == len(r["poses"]) and np.abs(o["poses"] - r["poses"]).max() < 1e-12
+    # degenerate frames: no features at all in one frame -> that pair and the next are skipped (n_circ < 3), like :1283-1288
+    empty = dict(kpL=np.zeros((0, 2), np.float32), kpR=np.zeros((0, 2), np.float32), dL=np.zeros((0, 121), np.float32),
+                 dR=np.zeros((0, 121), np.float32))
+    fr2 = [frames[0], frames[1], empty, frames[2], frames[3]]
+    seeds2 = make_seeds(len(fr2), H)
+    o = oracle.sequence(fr2, P1, P2, oracle.param_default(ransac_iter=H), seeds2)
+    r = ref.pipeline(fr2, P1, P2, H, seeds2)
+    for k in ("ok", "n_inliers", "n_circ"):
+        assert np.array_equal(o["records"][k], r["records"][k]), k
+    assert list(o["records"]["ok"]) == [0, 1, 0, 0, 1]
+
+
 # ------------------------------------------------------------------------------------------------ mvg / estimation.cpp
 
 def test_mvg_and_rigid_motion(oracle, ref):
