@@ -266,6 +266,10 @@ int viso_chain_poses(const viso_record* records, int n_frames, double* poses /* 
 int viso_seq_stats(viso_seq* seq, int64_t* match_bytes, int64_t* sad_pairs, int64_t* sad_evaluated);
 /* elapsed ms of the sad_match kernel in the last run (CUDA events on the context stream) */
 int viso_seq_match_ms(viso_seq* seq, float* ms);
+/* Measurement hook: launch ONLY the stereo (which = 0) or ONLY the temporal (which = 1) match_desc jobs of an already run
+ * sequence again and return the device time of that launch (CUDA events), the (query, candidate) pairs that reached the
+ * SAD and the queries the tile kernel left to the generic kernel.  Results are rewritten with identical values. */
+int viso_seq_time_match(viso_seq* seq, int which, float* ms, int64_t* sad_pairs, int32_t* n_pending);
 /* queries of the last submission that the tile kernel left to the generic kernel (top-K cut needed, candidate list or
  * staging buffer too small): a performance diagnostic, results do not depend on it */
 int viso_seq_last_pending(viso_seq* seq, int32_t* n_pending);

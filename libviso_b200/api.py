@@ -469,6 +469,12 @@ class Sequence:
         self.ctx._ck(lib().viso_seq_stats(self.h, C.byref(mb), C.byref(sp), C.byref(se)))
         return mb.value, sp.value, se.value
 
+    def time_match(self, which):
+        """device ms of a launch of only the stereo (0) / temporal (1) match jobs; returns (ms, sad_pairs, n_pending)"""
+        ms = C.c_float(0); sp = C.c_int64(0); npend = C.c_int32(0)
+        self.ctx._ck(lib().viso_seq_time_match(self.h, int(which), C.byref(ms), C.byref(sp), C.byref(npend)))
+        return ms.value, sp.value, npend.value
+
     def last_pending(self):
         n = C.c_int32(0)
         self.ctx._ck(lib().viso_seq_last_pending(self.h, C.byref(n)))

@@ -35,6 +35,8 @@ struct viso_seq {
     PackJob* pack_jobs = nullptr;
     GridJob* grid_jobs = nullptr;
     MatchJob* match_jobs = nullptr;
+    MatchJob* match_jobs_stereo = nullptr;   /* [F] the stereo jobs alone, [2(F-1)] the temporal jobs alone: viso_seq_time_match */
+    MatchJob* match_jobs_temporal = nullptr;
     SortJob* sort_jobs = nullptr;
     CircleJob* circ_jobs = nullptr;
     RansacProb* probs = nullptr;
@@ -129,7 +131,7 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     SA(hyp_tr, F * H * 6); SA(scratch, F * cap * 28);
     SA(hyp_ok, F * H); SA(hyp_count, F * H); SA(inliers, F * cap); SA(active, F * cap);
     SA(rec, F); SA(seeds, F * H * 3);
-    SA(pack_jobs, 2 * F); SA(grid_jobs, 2 * F); SA(match_jobs, 3 * F); SA(sort_jobs, F); SA(circ_jobs, F); SA(probs, F);
+    SA(pack_jobs, 2 * F); SA(grid_jobs, 2 * F); SA(match_jobs, 3 * F); SA(match_jobs_stereo, F); SA(match_jobs_temporal, 2 * F); SA(sort_jobs, F); SA(circ_jobs, F); SA(probs, F);
     SA(pairs, 2); SA(err, 1); SA(pending, 1); SA(pend_rec, VISO_SEQ_PENDING_CAP); SA(pend_job, VISO_SEQ_PENDING_CAP); SA(from_image, F); SA(extract_jobs, 2 * F);
 #undef SA
     if (cudaMallocHost(&s->h_nL, 4 * F * sizeof(int)) != cudaSuccess) {
@@ -160,7 +162,7 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     /* job tables: all pointers are fixed for the life of the object */
     std::vector<PackJob> pj(2 * F);
     std::vector<GridJob> gj(2 * F);
-    std::vector<MatchJob> mj;
+    std::vector<MatchJob> mj, mjs, mjt;
     std::vector<SortJob> sj(F);
     std::vector<CircleJob> cj(F);
     s->h_probs.resize(F);
@@ -184,12 +186,12 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
         MatchJob m;
         m.pad = 0;
         m.q = viewL(t); m.t = viewR(t); m.out = s->dense_lr + t * cap; m.mode = 0; /* stereo, viso.cpp:1240 */
-        mj.push_back(m);
+        mj.push_back(m); mjs.push_back(m);
         if (t > 0) {
             m.q = viewL(t); m.t = viewL(t - 1); m.out = s->dense_11 + t * cap; m.mode = 1; /* viso.cpp:1264 */
-            mj.push_back(m);
+            mj.push_back(m); mjt.push_back(m);
             m.q = viewR(t); m.t = viewR(t - 1); m.out = s->dense_22 + t * cap; m.mode = 1; /* viso.cpp:1275 */
-            mj.push_back(m);
+            mj.push_back(m); mjt.push_back(m);
         }
         SortJob& so = sj[t];
         so.dense = s->dense_lr + t * cap; so.n = s->nL + t; so.kp1 = s->kpL + t * cap; so.kp2 = s->kpR + t * cap;
@@ -216,6 +218,8 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     if ((e = cudaMemcpyAsync(s->pack_jobs, pj.data(), pj.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "cudaMemcpyAsync");
     if ((e = cudaMemcpyAsync(s->grid_jobs, gj.data(), gj.size() * sizeof(GridJob), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "cudaMemcpyAsync");
     if ((e = cudaMemcpyAsync(s->match_jobs, mj.data(), mj.size() * sizeof(MatchJob), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "cudaMemcpyAsync");
+    if ((e = cudaMemcpyAsync(s->match_jobs_stereo, mjs.data(), mjs.size() * sizeof(MatchJob), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "cudaMemcpyAsync");
+    if (!mjt.empty() && (e = cudaMemcpyAsync(s->match_jobs_temporal, mjt.data(), mjt.size() * sizeof(MatchJob), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "cudaMemcpyAsync");
     if ((e = cudaMemcpyAsync(s->sort_jobs, sj.data(), sj.size() * sizeof(SortJob), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "cudaMemcpyAsync");
     if ((e = cudaMemcpyAsync(s->circ_jobs, cj.data(), cj.size() * sizeof(CircleJob), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "cudaMemcpyAsync");
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");
@@ -685,6 +689,42 @@ int viso_seq_match_ms(viso_seq* s, float* ms)
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(s->ev1));
     CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    return VISO_OK;
+}
+
+int viso_seq_time_match(viso_seq* s, int which, float* ms, int64_t* sad_pairs, int32_t* n_pending)
+{
+    if (!s) return VISO_ERR_ARG;
+    viso_ctx* ctx = s->ctx;
+    if (!ms || which < 0 || which > 1) return ctx->fail(VISO_ERR_ARG, "seq_time_match: bad argument");
+    if (!s->ran || s->run_hi_total < s->F) return ctx->fail(VISO_ERR_ARG, "seq_time_match: run the whole sequence first");
+    if (which == 1 && s->F < 2) return ctx->fail(VISO_ERR_ARG, "seq_time_match: temporal jobs need two frames");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int max_n = 0;
+    for (int t = 0; t < s->F; ++t) max_n = std::max(max_n, std::max(s->h_nL[t], s->h_nR[t]));
+    viso_match_params ms_, mt_;
+    viso_match_params_stereo(&ms_, s->Fm);
+    viso_match_params_temporal(&mt_);
+    MatchParamsPair mp;
+    mp.p[0] = make_match_dev(&ms_);
+    mp.p[1] = make_match_dev(&mt_);
+    const MatchJob* jobs = which == 0 ? s->match_jobs_stereo : s->match_jobs_temporal;
+    const int nj = which == 0 ? s->F : 2 * (s->F - 1);
+    int nl = 0;
+    CK(viso_launch_zero(s->pairs, 4, st));
+    CK(cudaEventRecord(s->ev0, st));
+    CK(viso_launch_match(jobs, nj, max_n, max_n, mp, s->grid, s->pairs,
+                         PendingList{s->pending, s->pend_rec, s->pend_job, VISO_SEQ_PENDING_CAP}, ctx->match_mode, ctx->sm_count, st, &nl));
+    CK(cudaEventRecord(s->ev1, st));
+    ctx->launches += nl + 1;
+    CK(cudaEventSynchronize(s->ev1));
+    CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    unsigned long long p[2] = {0, 0};
+    CK(cudaMemcpyAsync(p, s->pairs, 16, cudaMemcpyDeviceToHost, st));
+    if (n_pending) CK(cudaMemcpyAsync(n_pending, s->pending, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (sad_pairs) *sad_pairs = (int64_t)p[0];
     return VISO_OK;
 }
 
