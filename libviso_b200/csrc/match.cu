@@ -717,6 +717,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     const int ql_stride = ql_cap + 2;
     __shared__ int qcnt[32];
     __shared__ int row_off[VISO_MAX_REG_ROWS + 1];
+    __shared__ int row_p0[VISO_MAX_REG_ROWS];
     __shared__ int tile_s[4];
     __shared__ uint4 qrec_s[32];
 
@@ -780,7 +781,6 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
             amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
         }
         const float grow = r + (1.0f + 4e-6f * (amax + r)) + 4e-6f * (amax + r) + 1e-3f;
-        const int cx0 = cell_coord(xmin - grow, g.gx), cx1 = cell_coord(xmax + grow, g.gx);
         const int cy0 = cell_coord(ymin - grow, g.gy), cy1 = cell_coord(ymax + grow, g.gy);
         const int nr = cy1 - cy0 + 1;
         int total = -1; /* -1: no staging */
@@ -788,22 +788,32 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
             int run = 0;
             for (int b = 0; b < nr; b += 32) {
                 const int rr = b + lane;
-                int len = 0;
+                int len = 0, p0 = 0;
                 if (rr < nr) {
+                    /* the reach that is left at this grid row's vertical distance from the box: the corners of the
+                     * bounding box are out of every query's L1 diamond and are not staged */
                     const int cy = cy0 + rr;
-                    len = __ldg(job.t.cell_start + cy * g.gx + cx1 + 1) - __ldg(job.t.cell_start + cy * g.gx + cx0);
+                    const float lo = (cy == 0) ? -CUDART_INF_F : (float)(cy * VISO_GRID_CS);
+                    const float hi = (cy == g.gy - 1) ? CUDART_INF_F : (float)((cy + 1) * VISO_GRID_CS);
+                    const float dymin = fmaxf(0.f, fmaxf(lo - ymax, ymin - hi));
+                    const float rem = grow - dymin;
+                    if (rem >= 0.f) {
+                        const int cx0 = cell_coord(xmin - rem, g.gx), cx1 = cell_coord(xmax + rem, g.gx);
+                        p0 = __ldg(job.t.cell_start + cy * g.gx + cx0);
+                        len = __ldg(job.t.cell_start + cy * g.gx + cx1 + 1) - p0;
+                    }
                 }
                 const int incl = warp_incl_scan(len, lane);
-                if (rr < nr) row_off[rr] = run + incl - len;
+                if (rr < nr) { row_off[rr] = run + incl - len; row_p0[rr] = p0; }
                 run += __shfl_sync(FULL, incl, 31);
             }
             if (lane == 0) row_off[nr] = run;
             if (run <= reg_cap) total = run;
         }
-        if (lane == 0) { tile_s[0] = cx0; tile_s[1] = cy0; tile_s[2] = nr; tile_s[3] = total; }
+        if (lane == 0) { tile_s[0] = 0; tile_s[1] = cy0; tile_s[2] = nr; tile_s[3] = total; }
     }
     __syncthreads();
-    const int rcx0 = tile_s[0], rcy0 = tile_s[1], nrows = tile_s[2];
+    const int nrows = tile_s[2];
     const bool tile_ok = tile_s[3] >= 0;
 
     unsigned pairs = 0;
@@ -817,7 +827,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
         const int R = tile_s[3];
         for (int rr = warp; rr < nrows; rr += VISO_MATCH_WARPS) {
             const int o = row_off[rr], len = row_off[rr + 1] - o;
-            const int p0 = __ldg(job.t.cell_start + (rcy0 + rr) * g.gx + rcx0);
+            const int p0 = row_p0[rr];
             const uint4* src = job.t.srec + p0;
             for (int i = lane; i < len; i += 32) { reg[o + i] = __ldg(src + i); regpos[o + i] = p0 + i; }
         }
@@ -1388,16 +1398,18 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
         const int tiles = ((g.gx + sc.tw - 1) / sc.tw) * ((g.gy + sc.th - 1) / sc.th);
         sad_match_staged_kernel<<<dim3(tiles, n_jobs), VISO_ST_WARPS * 32, st_smem, s>>>(jobs, mp, g, sc, sad_pairs, pend);
     } else {
-        /* staging capacity for a tile's neighbourhood: 1.5 x the expected point count of the grown tile box at the
-         * densest target set + 64, within [128, 6144] records of 16 bytes (shared memory not used here is L1 for the
-         * descriptor rows: measured 6.89 -> 6.72 ms against 2 x) */
+        /* staging capacity for a tile's neighbourhood: the expected point count of the grown tile box less its four
+         * corners (out of every query's reach, not staged) at the densest target set, x 1.35 + 48, within [128, 6144]
+         * records.  Shared memory not used here is L1 for the descriptor rows. */
         const double ext_x = (double)g.gx * VISO_GRID_CS, ext_y = (double)g.gy * VISO_GRID_CS;
-        const double bx = fmin(ext_x, VISO_TILE_W * VISO_GRID_CS + 2.0 * (r + 2) + 2 * VISO_GRID_CS);
-        const double by = fmin(ext_y, VISO_TILE_H * VISO_GRID_CS + 2.0 * (r + 2) + 2 * VISO_GRID_CS);
-        double expect = (double)max_nt * (bx * by) / (ext_x * ext_y);
+        const double bx = fmin(ext_x, VISO_TILE_W * VISO_GRID_CS + 2.0 * (r + 2) + VISO_GRID_CS);
+        const double by = fmin(ext_y, VISO_TILE_H * VISO_GRID_CS + 2.0 * (r + 2) + VISO_GRID_CS);
+        const double area = fmax(0.25 * bx * by, bx * by - 1.4 * fmin((double)r * r, 0.25 * bx * by));
+        double expect = (double)max_nt * area / (ext_x * ext_y);
         if (!(expect >= 0)) expect = 0;
-        int cap = (int)fmin(6144.0, fmax(128.0, 1.5 * expect + 64.0));
-        cap = (cap + 63) & ~63;
+        static const double cap_scale = getenv("VISO_GATHER_CAP_SCALE") ? atof(getenv("VISO_GATHER_CAP_SCALE")) : 1.35;
+        int cap = (int)fmin(6144.0, fmax(128.0, cap_scale * expect + 48.0));
+        cap = (cap + 31) & ~31;
         /* per-query list capacity: 1.5 x the expected number of points in the L1 diamond (2 r^2) + 16, 64..256 */
         const double in_diamond = (double)max_nt * fmin(1.0, 2.0 * (double)r * r / (ext_x * ext_y));
         int ql_cap = (int)fmin(256.0, fmax(64.0, 1.5 * in_diamond + 16.0));
@@ -1405,6 +1417,10 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
         const size_t smem = (size_t)cap * (sizeof(uint4) + sizeof(int)) + (size_t)32 * (ql_cap + 2) * sizeof(unsigned short);
         if (smem > 48 * 1024) { /* per device, so set whenever it is needed (a process may drive several GPUs) */
             e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        if (const char* cv = getenv("VISO_GATHER_CARVEOUT")) { /* experiment knob: shared-memory carve-out in percent */
+            e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
             if (e != cudaSuccess) return e;
         }
         const int tiles = ((g.gx + VISO_TILE_W - 1) / VISO_TILE_W) * ((g.gy + VISO_TILE_H - 1) / VISO_TILE_H);
