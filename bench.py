@@ -509,7 +509,7 @@ def main():
 
     # the only collective: the records of every rank's sequences -> rank 0, from device memory, on the library's stream
     lib_stream = torch.cuda.ExternalStream(ctx.stream_ptr())
-    stage = torch.zeros((2, per_rank_max, words), dtype=torch.int32, device="cuda")
+    stage = torch.zeros((2, per_rank_max, words), dtype=torch.int32, device="cuda") if world > 1 else None
     gathered = [torch.zeros((per_rank_max, words), dtype=torch.int32, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
 
     def gather_on(stream, buf):
@@ -675,12 +675,13 @@ def main():
 
     # ---- max over ranks; every rank's own numbers ----
     mm = float(np.mean(match_ms))
-    tms = torch.tensor([dev_ms, e2e_ms or 0.0], dtype=torch.float64, device="cuda")
+    on = "cuda" if world > 1 else "cpu"   # one GPU: nothing of torch's runs on the device
+    tms = torch.tensor([dev_ms, e2e_ms or 0.0], dtype=torch.float64, device=on)
     mine = torch.tensor([dev_ms / args.steps, (e2e_ms or 0.0) / args.steps, mm, float(sad_pairs), float(clocks.get("sm_mhz") or 0.0),
                          float(n_pairs_rank), (h2d / ((e2e_ms or 1.0) / args.steps * 1e-3) / 1e9) if e2e_ms else 0.0,
-                         float(match_bytes), float(n_pending), float(sad_eval)], dtype=torch.float64, device="cuda")
-    per_rank = [torch.zeros_like(mine) for _ in range(world)]
+                         float(match_bytes), float(n_pending), float(sad_eval)], dtype=torch.float64, device=on)
     if world > 1:
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(per_rank, mine)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         # rank 0 chains poses from the gathered records of the last resident step (viso.cpp:1313-1321)

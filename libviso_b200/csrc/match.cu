@@ -690,7 +690,7 @@ __device__ __forceinline__ void pend_push(const PendingList& pend, const uint4& 
 
 /*
  * sad_match_kernel: match_desc (viso.cpp:668-722) for a batch of jobs.  blockIdx.y = job, blockIdx.x = query tile
- * (VISO_TILE_W x VISO_TILE_H cells of the QUERY set's grid, 96 x 64 px).
+ * (TW x TH cells of the QUERY set's grid: 6 x 4 = 96 x 64 px).
  *
  * 1. Staging.  The candidate records (x, y, index, row sum) of every target cell that can hold a neighbour of any of
  *    the tile's queries -- the bounding box of the tile's query coordinates grown by radius + slack, clamped exactly
@@ -705,6 +705,7 @@ __device__ __forceinline__ void pend_push(const PendingList& pend, const uint4& 
  * kernel sad_match_generic_kernel, launched right after, completes exactly those (and exits at once when there are
  * none).
  */
+template <int TW, int TH>
 __global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, VISO_MATCH_MINB)
 sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, int reg_cap, int ql_cap,
                  unsigned long long* sad_pairs, PendingList pend)
@@ -725,17 +726,17 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     const MatchParamsDev& P = mp.p[job.mode];
     const int nq = *job.q.n, nt = *job.t.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_x = (g.gx + VISO_TILE_W - 1) / VISO_TILE_W;
+    const int tiles_x = (g.gx + TW - 1) / TW;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    if (ty * VISO_TILE_H >= g.gy || nq <= 0) return;
+    if (ty * TH >= g.gy || nq <= 0) return;
 
     /* the tile's queries: one span of the cell-sorted query array per cell row */
-    const int cx_lo = tx * VISO_TILE_W, cx_hi = min(cx_lo + VISO_TILE_W, g.gx);
+    const int cx_lo = tx * TW, cx_hi = min(cx_lo + TW, g.gx);
     int qtot = 0;
-    int qs[VISO_TILE_H], ql[VISO_TILE_H];
+    int qs[TH], ql[TH];
 #pragma unroll
-    for (int rr = 0; rr < VISO_TILE_H; ++rr) {
-        const int cy = ty * VISO_TILE_H + rr;
+    for (int rr = 0; rr < TH; ++rr) {
+        const int cy = ty * TH + rr;
         qs[rr] = 0; ql[rr] = 0;
         if (cy < g.gy) {
             qs[rr] = __ldg(job.q.cell_start + cy * g.gx + cx_lo);
@@ -748,7 +749,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
     auto query_rec = [&](int k) {
         int pos = 0;
 #pragma unroll
-        for (int rr = 0; rr < VISO_TILE_H; ++rr) {
+        for (int rr = 0; rr < TH; ++rr) {
             if (k >= 0 && k < ql[rr]) pos = qs[rr] + k;
             k -= ql[rr];
         }
@@ -1370,7 +1371,23 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
     /* the generic kernel loops over query chunks: about 16 CTAs per SM in total, never more than one per chunk */
     const int gchunks = (max_nq + VISO_STRIP_QPC - 1) / VISO_STRIP_QPC;
     const dim3 ggrid(std::min(gchunks, std::max(1, (sm_count * 16 + n_jobs - 1) / n_jobs)), n_jobs);
+    /* Dense target sets -- the expected number of points in a query's L1 diamond (2 r^2) exceeds half of max_neighbors,
+     * so most queries need the exact (L1, index) top-K cut of viso.cpp:180-186 -- go to the generic kernel at once:
+     * measured at 20 000 keypoints per image (BASELINE configs[2]) 0.21 / 0.31 ms per stereo / temporal match_desc call
+     * against 0.33 / 0.42 ms for "tile kernel first, then every query pending" and 0.34 / 0.50 ms for running the
+     * top-K selection inside the tile kernel on the staged records (2 x 2-cell tiles; removed again). */
+    {
+        const float rr = fmaxf(mp.p[0].radius, mp.p[1].radius);
+        const double ext = (double)g.gx * VISO_GRID_CS * (double)g.gy * VISO_GRID_CS;
+        const double in_diamond = rr >= 0.f ? (double)max_nt * fmin(1.0, 2.0 * (double)rr * rr / ext) : 0.0;
+        if (mode == VISO_MATCH_AUTO && in_diamond > 0.5 * std::min(mp.p[0].K, mp.p[1].K)) mode = VISO_MATCH_GENERIC;
+    }
     if (mode == VISO_MATCH_GENERIC) {
+        if (pend.count) { /* the counter is reported by viso_seq_last_pending: nothing is pending on this path */
+            cudaError_t ez = viso_launch_zero(pend.count, 1, s);
+            if (ez != cudaSuccess) return ez;
+            if (launches) *launches += 1;
+        }
         sad_match_generic_kernel<<<ggrid, VISO_MATCH_WARPS * 32, 0, s>>>(jobs, mp, g, sad_pairs, pend, 0);
         if (launches) *launches += 1;
         return cudaGetLastError();
@@ -1402,29 +1419,32 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
          * corners (out of every query's reach, not staged) at the densest target set, x 1.35 + 48, within [128, 6144]
          * records.  Shared memory not used here is L1 for the descriptor rows. */
         const double ext_x = (double)g.gx * VISO_GRID_CS, ext_y = (double)g.gy * VISO_GRID_CS;
-        const double bx = fmin(ext_x, VISO_TILE_W * VISO_GRID_CS + 2.0 * (r + 2) + VISO_GRID_CS);
-        const double by = fmin(ext_y, VISO_TILE_H * VISO_GRID_CS + 2.0 * (r + 2) + VISO_GRID_CS);
+        /* per-query list capacity: 1.5 x the expected number of points in the L1 diamond (2 r^2) + 16, 64..256 */
+        const double in_diamond = (double)max_nt * fmin(1.0, 2.0 * (double)r * r / (ext_x * ext_y));
+        const int tw = VISO_TILE_W, th = VISO_TILE_H;
+        const double bx = fmin(ext_x, tw * VISO_GRID_CS + 2.0 * (r + 2) + VISO_GRID_CS);
+        const double by = fmin(ext_y, th * VISO_GRID_CS + 2.0 * (r + 2) + VISO_GRID_CS);
         const double area = fmax(0.25 * bx * by, bx * by - 1.4 * fmin((double)r * r, 0.25 * bx * by));
         double expect = (double)max_nt * area / (ext_x * ext_y);
         if (!(expect >= 0)) expect = 0;
         static const double cap_scale = getenv("VISO_GATHER_CAP_SCALE") ? atof(getenv("VISO_GATHER_CAP_SCALE")) : 1.35;
         int cap = (int)fmin(6144.0, fmax(128.0, cap_scale * expect + 48.0));
         cap = (cap + 31) & ~31;
-        /* per-query list capacity: 1.5 x the expected number of points in the L1 diamond (2 r^2) + 16, 64..256 */
-        const double in_diamond = (double)max_nt * fmin(1.0, 2.0 * (double)r * r / (ext_x * ext_y));
         int ql_cap = (int)fmin(256.0, fmax(64.0, 1.5 * in_diamond + 16.0));
         ql_cap = (ql_cap + 31) & ~31;
-        const size_t smem = (size_t)cap * (sizeof(uint4) + sizeof(int)) + (size_t)32 * (ql_cap + 2) * sizeof(unsigned short);
-        if (smem > 48 * 1024) { /* per device, so set whenever it is needed (a process may drive several GPUs) */
-            e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        if (const char* cv = getenv("VISO_GATHER_CARVEOUT")) { /* experiment knob: shared-memory carve-out in percent */
-            e = cudaFuncSetAttribute(sad_match_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
-            if (e != cudaSuccess) return e;
-        }
-        const int tiles = ((g.gx + VISO_TILE_W - 1) / VISO_TILE_W) * ((g.gy + VISO_TILE_H - 1) / VISO_TILE_H);
-        sad_match_kernel<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, ql_cap, sad_pairs, pend);
+        const size_t list_bytes = (size_t)32 * (ql_cap + 2) * sizeof(unsigned short);
+        const size_t smem = (size_t)cap * (sizeof(uint4) + sizeof(int)) + list_bytes;
+        const int tiles = ((g.gx + tw - 1) / tw) * ((g.gy + th - 1) / th);
+        auto launch = [&](auto kern) -> cudaError_t {
+            if (smem > 48 * 1024) { /* per device, so set whenever it is needed (a process may drive several GPUs) */
+                cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e2 != cudaSuccess) return e2;
+            }
+            kern<<<dim3(tiles, n_jobs), VISO_MATCH_WARPS * 32, smem, s>>>(jobs, mp, g, cap, ql_cap, sad_pairs, pend);
+            return cudaSuccess;
+        };
+        e = launch(sad_match_kernel<VISO_TILE_W, VISO_TILE_H>);
+        if (e != cudaSuccess) return e;
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

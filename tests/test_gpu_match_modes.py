@@ -43,6 +43,8 @@ def test_modes_synthetic_frames(mctx, api, oracle, small_sequence):
     (2000, 1241, 376, 250, 80.0, True),    # the pipeline's density: everything stays on the tile kernels
     (2000, 1241, 376, 250, 80.0, False),   # float coordinates
     (3000, 400, 300, 250, 80.0, True),     # dense: the top-K cut binds, queries go through the pending list
+    (6000, 640, 200, 250, 80.0, True),     # dense everywhere: the gather kernel runs match_query on the staged records
+    (5000, 640, 200, 40, 80.0, False),     # the same with float coordinates and a small K
     (1200, 640, 200, 40, 30.0, True),      # small radius, small K
     (600, 1241, 376, 250, 500.0, True),    # radius beyond the image: neighbourhood = everything
     (300, 200, 120, 250, 0.0, True),       # radius 0
