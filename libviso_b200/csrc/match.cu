@@ -393,11 +393,19 @@ struct TileAcc { /* region indices into the staged neighbourhood (tile kernel): 
     }
 };
 
+/* a * one + c as one IMAD: inline PTX so that the front end cannot factor the multiplier out of a chain of them */
+__device__ __forceinline__ unsigned imad1(unsigned a, unsigned one, unsigned c)
+{
+    unsigned d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
+    return d;
+}
+
 /* NB = butterfly width in steps (8: up to 32 candidates, 4: up to 16), NL <= NB = steps whose rows are actually
  * loaded and evaluated (the rest contribute 0 and are masked) */
 template <int NB, int NL, class Acc>
 __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, const Acc& acc_, int base, int n, int lane,
-                                           const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
+                                           const uint4& qa, const uint4& qb, unsigned qsum, BestState& st, unsigned one)
 {
     const int sub = lane & 7, g = lane >> 3;
     const bool b0 = sub & 1, b1 = sub & 2, b2 = sub & 4;
@@ -422,43 +430,51 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
 #pragma unroll
         for (int s = 0; s < VISO_EVAL_DEPTH; ++s) {
             if (h + s < NL) {
-                const unsigned acc = __vminu2(qa.x, ra[s].x) + __vminu2(qa.y, ra[s].y) + __vminu2(qa.z, ra[s].z) + __vminu2(qa.w, ra[s].w) +
-                                     __vminu2(qb.x, rb[s].x) + __vminu2(qb.y, rb[s].y) + __vminu2(qb.z, rb[s].z) + __vminu2(qb.w, rb[s].w);
-                part[h + s] = (acc & 0xffffu) + (acc >> 16); /* 16 elements x 2047 < 65536: no carry between halves */
+                /* min on the ALU pipe, the running sum on the FMA pipe (IMAD with the opaque multiplier `one`): with
+                 * 3-input adds everything went down the ALU pipe, which was the kernel's limiter (IPC 2.45 of 4).
+                 * Packed u16x2 sums: 16 elements x 2047 per half < 65536, no carry between halves */
+                unsigned a0 = __vminu2(qa.x, ra[s].x), a1 = __vminu2(qb.x, rb[s].x);
+                a0 = imad1(__vminu2(qa.y, ra[s].y), one, a0); a1 = imad1(__vminu2(qb.y, rb[s].y), one, a1);
+                a0 = imad1(__vminu2(qa.z, ra[s].z), one, a0); a1 = imad1(__vminu2(qb.z, rb[s].z), one, a1);
+                a0 = imad1(__vminu2(qa.w, ra[s].w), one, a0); a1 = imad1(__vminu2(qb.w, rb[s].w), one, a1);
+                part[h + s] = imad1(a1, one, a0);
             }
         }
     }
     /* transposed reduction over the 8 lanes of a row group: lane (g, sub) ends with candidate 4*step + g where
      * step = sub (NB = 8) or sub & 3 (NB = 4; lanes sub and sub^4 then hold the same candidate) */
+    /* the first stage adds two packed sums (2 x 32752 per half still fits); the halves are folded after it */
     unsigned r2[2];
     if (NB == 8) {
         unsigned r4[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const unsigned lo = part[2 * j], hi = part[2 * j + 1];
-            r4[j] = (b0 ? hi : lo) + __shfl_xor_sync(FULL, b0 ? lo : hi, 1);
+            const unsigned t = imad1(__shfl_xor_sync(FULL, b0 ? lo : hi, 1), one, b0 ? hi : lo);
+            r4[j] = imad1(t >> 16, one, t & 0xffffu);
         }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const unsigned lo = r4[2 * j], hi = r4[2 * j + 1];
-            r2[j] = (b1 ? hi : lo) + __shfl_xor_sync(FULL, b1 ? lo : hi, 2);
+            r2[j] = imad1(__shfl_xor_sync(FULL, b1 ? lo : hi, 2), one, b1 ? hi : lo);
         }
     } else {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const unsigned lo = part[2 * j], hi = part[2 * j + 1];
-            r2[j] = (b0 ? hi : lo) + __shfl_xor_sync(FULL, b0 ? lo : hi, 1);
+            const unsigned t = imad1(__shfl_xor_sync(FULL, b0 ? lo : hi, 1), one, b0 ? hi : lo);
+            r2[j] = imad1(t >> 16, one, t & 0xffffu);
         }
     }
     unsigned tot;
     int slot; /* position of this lane's candidate inside the batch */
     bool mine = true;
     if (NB == 8) {
-        tot = (b2 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b2 ? r2[0] : r2[1], 4);
+        tot = imad1(__shfl_xor_sync(FULL, b2 ? r2[0] : r2[1], 4), one, b2 ? r2[1] : r2[0]);
         slot = 4 * sub + g;
     } else {
-        const unsigned t2 = (b1 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b1 ? r2[0] : r2[1], 2);
-        tot = t2 + __shfl_xor_sync(FULL, t2, 4);
+        const unsigned t2 = imad1(__shfl_xor_sync(FULL, b1 ? r2[0] : r2[1], 2), one, b1 ? r2[1] : r2[0]);
+        tot = imad1(__shfl_xor_sync(FULL, t2, 4), one, t2);
         slot = 4 * (sub & 3) + g;
         mine = !b2; /* the duplicate lanes sit out */
     }
@@ -489,15 +505,15 @@ __device__ __forceinline__ void eval_batch(const uint4* __restrict__ tbase, cons
 
 template <class Acc>
 __device__ __forceinline__ void eval_list(const uint16_t* __restrict__ tdesc, const Acc& acc, int n, int lane,
-                                          const uint4& qa, const uint4& qb, unsigned qsum, BestState& st)
+                                          const uint4& qa, const uint4& qb, unsigned qsum, BestState& st, unsigned one)
 {
     const uint4* tbase = reinterpret_cast<const uint4*>(tdesc) + (lane & 7);
     int base = 0;
-    for (; n - base > 24; base += 32) eval_batch<8, 8>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+    for (; n - base > 24; base += 32) eval_batch<8, 8>(tbase, acc, base, n, lane, qa, qb, qsum, st, one);
     const int rest = n - base; /* 0..24: rows are loaded in units of 8 candidates */
-    if (rest > 16) eval_batch<8, 6>(tbase, acc, base, n, lane, qa, qb, qsum, st);
-    else if (rest > 8) eval_batch<4, 4>(tbase, acc, base, n, lane, qa, qb, qsum, st);
-    else if (rest > 0) eval_batch<4, 2>(tbase, acc, base, n, lane, qa, qb, qsum, st);
+    if (rest > 16) eval_batch<8, 6>(tbase, acc, base, n, lane, qa, qb, qsum, st, one);
+    else if (rest > 8) eval_batch<4, 4>(tbase, acc, base, n, lane, qa, qb, qsum, st, one);
+    else if (rest > 0) eval_batch<4, 2>(tbase, acc, base, n, lane, qa, qb, qsum, st, one);
 }
 
 /* viso.cpp:711-722: the ratio test and the dense output record (best_idx, best_d1, best_d2, valid) */
@@ -535,7 +551,7 @@ __device__ __forceinline__ void write_result(const MatchJob& job, const MatchPar
  */
 template <class V>
 __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, const MatchParamsDev& P, WarpScratch& ws,
-                                                int lane, const uint4 qrec)
+                                                int lane, const uint4 qrec, unsigned one)
 {
     const int q = (int)qrec.z;
     const float qx = __uint_as_float(qrec.x), qy = __uint_as_float(qrec.y);
@@ -665,7 +681,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
         nlist += __popc(tm);
         if (nlist > VISO_LIST_CAP - 32) {
             __syncwarp();
-            eval_list(job.t.desc, ListAcc{ws}, nlist, lane, qa, qb, qsum, st);
+            eval_list(job.t.desc, ListAcc{ws}, nlist, lane, qa, qb, qsum, st, one);
             pairs += nlist;
             nlist = 0;
             __syncwarp();
@@ -673,7 +689,7 @@ __device__ __forceinline__ unsigned match_query(V& vis, const MatchJob& job, con
     });
     if (nlist > 0) {
         __syncwarp();
-        eval_list(job.t.desc, ListAcc{ws}, nlist, lane, qa, qb, qsum, st);
+        eval_list(job.t.desc, ListAcc{ws}, nlist, lane, qa, qb, qsum, st, one);
         pairs += nlist;
         __syncwarp();
     }
@@ -890,7 +906,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                         if (take) {
                             const uint4 rec = reg[ri];
                             const double sd = sampson_dev(P.F, qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
-                            if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
+            if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
                         }
                         const unsigned tm = __ballot_sync(FULL, take);
                         __syncwarp(); /* every lane has read its entry before the slots are reused */
@@ -899,7 +915,7 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
                     }
                     __syncwarp();
                 }
-                if (nlist > 0) eval_list(job.t.desc, TileAcc{ql, reg, regpos, qx, qy}, nlist, lane, qa, qb, qrec.w, st);
+                if (nlist > 0) eval_list(job.t.desc, TileAcc{ql, reg, regpos, qx, qy}, nlist, lane, qa, qb, qrec.w, st, g.one);
                 pairs += nlist;
                 if (lane == 0) write_result(job, P, q, st);
             }
@@ -934,7 +950,7 @@ sad_match_generic_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, 
             return;
         }
         GlobalVisitor vis{job.t, g, make_geom(g, __uint_as_float(qrec.x), __uint_as_float(qrec.y), P.radius), ws, lane, 0, true};
-        pairs += match_query(vis, job, P, ws, lane, qrec);
+        pairs += match_query(vis, job, P, ws, lane, qrec, g.one);
     };
     if (only_pending && pend.rec && np <= pend.cap) {
         /* the listed queries, spread over all CTAs of the grid (entry e goes to CTA e mod #CTAs) */
@@ -1214,7 +1230,7 @@ sad_match_staged_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, G
                     if (take) {
                         const uint4 rec = reg[ri];
                         const double sd = sampson_dev(P.F, qx, qy, __uint_as_float(rec.x), __uint_as_float(rec.y));
-                        if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
+            if (!isfinite(sd) || sd > P.sampson_thresh) take = false;
                     }
                     const unsigned tm = __ballot_sync(FULL, take);
                     __syncwarp(); /* every lane has read its entry before the slots are reused */

@@ -42,7 +42,9 @@
 #define VISO_PENDING (-2)         /* dense result .w: left by the tile kernel for the generic kernel */
 #define VISO_MAX_REG_ROWS 64     /* grid rows a staged tile neighbourhood may span */
 
-struct GridCfg { int gx, gy; };
+/* `one` is always 1: a multiplier the compiler cannot see through, so that `a * one + b` stays an IMAD (FMA pipe) where the
+ * ALU pipe is the busy one (match.cu, eval_batch) */
+struct GridCfg { int gx, gy; unsigned one = 1; };
 
 struct SetView {
     const float2* xy;        /* original order */
