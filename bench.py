@@ -303,23 +303,72 @@ class StdoutGuard:
         os.dup2(2, 1)
 
 
-def bind_to_gpu_cpus(local_rank):
+def gpu_uuid(dev):
+    """'GPU-...' of CUDA device `dev` (what nvidia-smi -i and NVML take), or None with an older torch"""
+    try:
+        import torch
+        u = getattr(torch.cuda.get_device_properties(dev), "uuid", None)
+        return None if u is None else ("GPU-" + str(u) if not str(u).startswith("GPU-") else str(u))
+    except Exception:
+        return None
+
+
+def nvml_handle(dev):
+    import pynvml
+    pynvml.nvmlInit()
+    u = gpu_uuid(dev)
+    if u:
+        try:
+            return pynvml.nvmlDeviceGetHandleByUUID(u.encode() if hasattr(u, "encode") else u)
+        except Exception:
+            pass
+    idx = dev
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [v for v in vis.split(",") if v.strip()]
+        if dev < len(ids) and ids[dev].strip().isdigit():
+            idx = int(ids[dev])
+    return pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+
+def gpu_cpus(dev):
+    """the CPUs NVML calls local to CUDA device `dev` (its NUMA node)"""
+    import pynvml
+    words = ((os.cpu_count() or 64) + 63) // 64
+    mask = pynvml.nvmlDeviceGetCpuAffinity(nvml_handle(dev), words)
+    return frozenset(64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1)
+
+
+def pick_device(local_rank, world, n_visible):
+    """CUDA device of this rank.  With as many visible GPUs as ranks: device = local rank.  With more (a 4-rank run on
+    an 8-GPU box), the ranks are dealt round-robin over the GPUs' NUMA nodes instead of packed onto the first node: the
+    end-to-end path streams ~1 GB per sequence per step from pinned host memory, and four copy streams behind one
+    socket's memory and PCIe root measured 27.7 GB/s each against 51.7 GB/s for two (profiles/r02_g_bench_n4/n2).
+    Every rank computes the same order, so the devices are distinct.  The device-resident numbers do not depend on it."""
+    if n_visible <= world or os.environ.get("VISO_BENCH_PACK_GPUS"):
+        return local_rank, "device = local rank"
+    try:
+        groups = {}
+        for d in range(n_visible):
+            groups.setdefault(gpu_cpus(d), []).append(d)
+        if len(groups) < 2:
+            # a VM shows one node whatever the board looks like (the 8-GPU boxes of this pool do: GPUs 0-3 then measure
+            # 21 GB/s each and GPUs 4-7 31 GB/s with all eight copying): spread the ranks evenly over the device indices,
+            # adjacent indices being the ones that share a PCIe switch / root on HGX boards
+            stride = n_visible // world
+            return local_rank * stride, "ranks spread over the %d visible GPUs with stride %d" % (n_visible, stride)
+        lists = sorted(groups.values(), key=lambda g: g[0])
+        order = [g[i] for i in range(max(len(g) for g in lists)) for g in lists if i < len(g)]
+        return order[local_rank], "ranks dealt round-robin over %d NUMA nodes: %s" % (len(lists), order[:world])
+    except Exception as e:  # no NVML: keep the plain mapping
+        return local_rank, "device = local rank (%s)" % e
+
+
+def bind_to_gpu_cpus(dev):
     """The pinned host buffers are first-touched by this process: keep it on the CPUs (NUMA node) next to its GPU.
     A no-op where NVML reports every CPU (single-socket boxes)."""
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        idx = local_rank
-        if vis:
-            ids = [v for v in vis.split(",") if v.strip()]
-            if local_rank < len(ids) and ids[local_rank].strip().isdigit():
-                idx = int(ids[local_rank])
-        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-        words = ((os.cpu_count() or 64) + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
-        cpus &= os.sched_getaffinity(0)
+        cpus = set(gpu_cpus(dev)) & os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)
     except Exception as e:  # no NVML, restricted cpuset, ...: keep the inherited affinity
@@ -433,12 +482,13 @@ def main():
     build.build()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libviso_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    bind_to_gpu_cpus(local_rank)
+    dev, placement = pick_device(local_rank, world, torch.cuda.device_count())
+    torch.cuda.set_device(dev)
+    bind_to_gpu_cpus(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's own log lines: keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
 
     def barrier():
         if world > 1:
@@ -453,7 +503,7 @@ def main():
     use_img = args.input in ("images", "raw")
     use_raw = args.input == "raw"   # images only: keypoints detected on the device as well (viso.cpp:925-976)
 
-    ctx = api.Context(local_rank)
+    ctx = api.Context(dev)
     ctx.set_image_extent(synth.W, synth.H)
     param = api.param_default(ransac_iter=H)
     words = F * 16                                            # one record = 64 bytes = 16 int32 words
@@ -534,7 +584,7 @@ def main():
     ctx.sync()
     torch.cuda.synchronize()
     l0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(gpu_uuid(dev) or dev)
     barrier()
     sampler.start()
     match_ms = []
@@ -589,7 +639,7 @@ def main():
         # records back inside the timed region; with N > 1 the step's records are also gathered from device memory.
         lanes = [(ctx, data[0]["seq"])]
         if args.e2e_buffers > 1:
-            ctx2 = api.Context(local_rank)
+            ctx2 = api.Context(dev)
             ctx2.set_image_extent(synth.W, synth.H)
             if not args.e2e_separate_copy_streams:
                 ctx2.share_copy_stream(ctx)   # uploads of the two lanes are served FIFO, not interleaved
@@ -709,7 +759,7 @@ def main():
             "higher_is_better": True, "scaling": "strong" if (args.mode == "configs[4]" and world > 1) else "weak",
             "vs_baseline": None, "dtype": "u16 SAD / f64 pose",
             "data": "synthetic", "config": workload_config(args, world),
-            "clocks": clocks, "gpu_launches": int(launches),
+            "clocks": clocks, "gpu_launches": int(launches), "placement": placement,
             "per_rank": {k: [round(float(v), 3) for v in pr[:, i]]
                          for i, k in enumerate(("ms_per_step", "e2e_ms_per_step", "sad_ms_per_step", "sad_pairs", "sm_mhz",
                                                 "frame_pairs_per_step", "e2e_h2d_GBps"))},
