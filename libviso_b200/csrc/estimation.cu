@@ -316,7 +316,10 @@ __global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4, VISO_HYP_MINB) ransac_hy
 }
 
 /* One warp per hypothesis: support-set size, viso.cpp:1563 (get_inliers, :1509-1537) */
-__global__ void __launch_bounds__(256) ransac_score_kernel(const RansacProb* __restrict__ probs, ParamDev P)
+#ifndef VISO_SCORE_MINB
+#define VISO_SCORE_MINB 4 /* 64 registers, 32 warps per SM: the loop waits on L1-hit latency (long scoreboard), measured -0.08 ms per 1000 frames */
+#endif
+__global__ void __launch_bounds__(256, VISO_SCORE_MINB) ransac_score_kernel(const RansacProb* __restrict__ probs, ParamDev P)
 {
     const RansacProb& pb = probs[blockIdx.y];
     const int lane = threadIdx.x & 31;
@@ -485,7 +488,10 @@ __device__ int inliers_block(const double* __restrict__ X, const double* __restr
 }
 
 /* One CTA per problem: viso.cpp:1564-1579 */
-__global__ void __launch_bounds__(256) ransac_final_kernel(const RansacProb* __restrict__ probs, ParamDev P)
+#ifndef VISO_FINAL_MINB
+#define VISO_FINAL_MINB 2 /* 128 registers (spills in the row evaluation are hidden: the CTA waits on barriers and the sequential sums), -0.07 ms */
+#endif
+__global__ void __launch_bounds__(256, VISO_FINAL_MINB) ransac_final_kernel(const RansacProb* __restrict__ probs, ParamDev P)
 {
     __shared__ int warp_tot[32];
     __shared__ int best_cnt_s[256], best_idx_s[256];
