@@ -186,10 +186,11 @@ __constant__ int c_pair_a[27] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3,
 __constant__ int c_pair_b[27] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 6, 6, 6, 6, 6, 6};
 
 #ifndef VISO_HYP_PER_CTA
-#define VISO_HYP_PER_CTA 32 /* hypotheses per CTA of ransac_hyp_kernel: 4 lanes each */
+#define VISO_HYP_PER_CTA 8 /* hypotheses per CTA of ransac_hyp_kernel, 4 lanes each: one warp, so that a hypothesis that runs all 100
+                             iterations (0.8 % do, and the kernel lasts as long as they) holds one warp's registers, not four */
 #endif
 #ifndef VISO_HYP_MINB
-#define VISO_HYP_MINB 1
+#define VISO_HYP_MINB 12
 #endif
 
 /*
