@@ -625,6 +625,6 @@ __global__ void sincos_probe_kernel(const double* __restrict__ x, int n, double*
 cudaError_t viso_launch_sincos_probe(const double* x, int n, double* s, double* c, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    sincos_probe_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, st>>>(x, n, s, c);
+    sincos_probe_kernel<<<std::min((n + 255) / 256, 1024), 256, 0, st>>>(x, n, s, c); /* grid-stride test hook */
     return cudaGetLastError();
 }
