@@ -232,6 +232,12 @@ int64_t viso_seq_device_bytes(const viso_seq* seq);
  *   viso_seq_get_keypoints: the keypoints of frame t, side 0 (left) / 1 (right), after a run. */
 int viso_detect_harris(viso_ctx* ctx, const uint8_t* img, int width, int height, int pitch, int n_features, int nbinx,
                        int nbiny, float k, float* kp_xy, float* kp_response, int32_t* n_out);
+/* Tuning / test knob of the RANSAC hypothesis stage (viso.cpp:1555-1562): a three-point Gauss-Newton solve that has not
+ * converged after `cap` iterations moves from the four-lanes-per-hypothesis kernel to a warp-per-hypothesis kernel for
+ * iterations cap .. 99.  Results do not depend on it (same operations, differently spread over lanes); 100 keeps
+ * everything in the first kernel.  Default 8; VISO_HYP_IT_CAP in the environment at viso_create overrides it. */
+int viso_set_hyp_iteration_cap(viso_ctx* ctx, int cap);
+
 /* Test hook: sin(x[i]), cos(x[i]) as the estimation kernels evaluate them (glibc's algorithm, libviso_b200/csrc/
  * glibc_sincos.h): bit-identical to the host libm for |x| < 0x1.921fbp+26 = 105414336. */
 int viso_debug_sincos(viso_ctx* ctx, const double* x, int n, double* s, double* c);

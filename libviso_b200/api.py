@@ -335,6 +335,9 @@ class Context:
         return dict(ok=bool(ok.value), tr=tr, inliers=inl[:ni.value].copy(), hyp_tr=htr[:H], hyp_ok=hok[:H],
                     hyp_count=hc[:H], best_hyp=bh.value)
 
+    def set_hyp_iteration_cap(self, cap):
+        self._ck(lib().viso_set_hyp_iteration_cap(self.h, int(cap)))
+
     def debug_sincos(self, x):
         """sin / cos as the estimation kernels evaluate them (glibc's algorithm on the device)"""
         x = _f64(x).reshape(-1)

@@ -180,7 +180,16 @@ int viso_create(viso_ctx** out, int device)
     if (const char* m = getenv("VISO_MATCH_MODE")) /* generic | gather | staged: force one matching path (tests, A/B) */
         ctx->match_mode = m[0] == 'g' && m[1] == 'e' ? VISO_MATCH_GENERIC : m[0] == 'g' ? VISO_MATCH_GATHER
                           : m[0] == 's' ? VISO_MATCH_STAGED : VISO_MATCH_AUTO;
+    if (const char* c = getenv("VISO_HYP_IT_CAP")) ctx->hyp_it_cap = std::max(1, std::min(100, atoi(c)));
     *out = ctx;
+    return VISO_OK;
+}
+
+int viso_set_hyp_iteration_cap(viso_ctx* ctx, int cap)
+{
+    if (!ctx) return VISO_ERR_ARG;
+    if (cap < 1 || cap > 100) return ctx->fail(VISO_ERR_ARG, "set_hyp_iteration_cap: 1..100");
+    ctx->hyp_it_cap = cap;
     return VISO_OK;
 }
 
@@ -811,6 +820,7 @@ int viso_ransac_minimize_reproj(viso_ctx* ctx, const double* X, const double* ob
         int *n, *table, *hyp_ok, *hyp_count, *inliers, *active;
         viso_record_dev* rec;
         RansacProb* prob;
+        int* strag;
     } b;
     auto carve = [&](Carver& c) {
         b.X = c.take<double>((size_t)n * 3); b.obs = c.take<double>((size_t)n * 4);
@@ -818,6 +828,7 @@ int viso_ransac_minimize_reproj(viso_ctx* ctx, const double* X, const double* ob
         b.n = c.take<int>(1); b.table = c.take<int>((size_t)H * 3); b.hyp_ok = c.take<int>(H); b.hyp_count = c.take<int>(H);
         b.inliers = c.take<int>(n); b.active = c.take<int>(n);
         b.rec = c.take<viso_record_dev>(1); b.prob = c.take<RansacProb>(1);
+        b.strag = c.take<int>(2 + 2 * (size_t)H);
     };
     Carver measure(nullptr);
     carve(measure);
@@ -839,7 +850,7 @@ int viso_ransac_minimize_reproj(viso_ctx* ctx, const double* X, const double* ob
     for (int j = 0; j < 6; ++j) pb.tr_init[j] = tr[j];
     CK(cudaMemcpyAsync(b.prob, &pb, sizeof(pb), cudaMemcpyHostToDevice, s));
     int nl = 0;
-    CK(viso_launch_ransac(b.prob, 1, H, n, make_param_dev(param), s, &nl));
+    CK(viso_launch_ransac(b.prob, 1, H, n, make_param_dev(param), b.strag, ctx->hyp_it_cap, ctx->sm_count, s, &nl));
     ctx->launches += nl;
     viso_record_dev rec;
     CK(cudaMemcpyAsync(&rec, b.rec, sizeof(rec), cudaMemcpyDeviceToHost, s));

@@ -25,6 +25,7 @@ struct viso_ctx {
     cudaStream_t own_copy_stream = nullptr; /* the one this context created (copy_stream may be another context's) */
     int match_mode = VISO_MATCH_AUTO;     /* VISO_MATCH_* (viso_dev.h): which matching kernel path; VISO_MATCH_MODE at viso_create */
     int sm_count = 148;                   /* cudaDevAttrMultiProcessorCount of the device */
+    int hyp_it_cap = VISO_HYP_IT_CAP;     /* viso_set_hyp_iteration_cap / VISO_HYP_IT_CAP at viso_create (estimation.cu) */
 
     int fail(int code, const std::string& msg)
     {

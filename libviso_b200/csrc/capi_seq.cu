@@ -32,6 +32,7 @@ struct viso_seq {
     int *hyp_ok = nullptr, *hyp_count = nullptr, *inliers = nullptr, *active = nullptr;
     viso_record_dev* rec = nullptr;
     uint32_t* seeds = nullptr;
+    int* strag = nullptr;   /* hypotheses handed from the quad kernel to the warp-per-hypothesis kernel (estimation.cu) */
     PackJob* pack_jobs = nullptr;
     GridJob* grid_jobs = nullptr;
     MatchJob* match_jobs = nullptr;
@@ -132,6 +133,7 @@ int viso_seq_create(viso_ctx* ctx, int n_frames, int max_kp, int desc_len, int m
     SA(hyp_ok, F * H); SA(hyp_count, F * H); SA(inliers, F * cap); SA(active, F * cap);
     SA(rec, F); SA(seeds, F * H * 3);
     SA(pack_jobs, 2 * F); SA(grid_jobs, 2 * F); SA(match_jobs, 3 * F); SA(match_jobs_stereo, F); SA(match_jobs_temporal, 2 * F); SA(sort_jobs, F); SA(circ_jobs, F); SA(probs, F);
+    SA(strag, 2 + 2 * F * (size_t)std::max(max_ransac_iter, 1));
     SA(pairs, 2); SA(err, 1); SA(pending, 1); SA(pend_rec, VISO_SEQ_PENDING_CAP); SA(pend_job, VISO_SEQ_PENDING_CAP); SA(from_image, F); SA(extract_jobs, 2 * F);
 #undef SA
     if (cudaMallocHost(&s->h_nL, 4 * F * sizeof(int)) != cudaSuccess) {
@@ -595,7 +597,7 @@ int viso_seq_run_range(viso_seq* s, const viso_param* param, int t0, int t1)
     if (t1 > c0) {
         CK(viso_launch_circle(s->circ_jobs + c0, t1 - c0, st));
         ++nl;
-        CK(viso_launch_ransac(s->probs + c0, t1 - c0, param->ransac_iter, max_nL, pd, st, &nl));
+        CK(viso_launch_ransac(s->probs + c0, t1 - c0, param->ransac_iter, max_nL, pd, s->strag, ctx->hyp_it_cap, ctx->sm_count, st, &nl));
     }
     ctx->launches += nl;
     CK(cudaEventRecord(s->ev_compute, st));

@@ -12,6 +12,7 @@
 #include "glibc_sincos.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 /* ------------------------------------------------------------------------------------------------ estimation */
 
@@ -23,13 +24,11 @@ struct Rot {
     double tx, ty, tz;
 };
 
-/* viso.cpp:1406-1424 */
-__device__ __forceinline__ void make_rot(const double* tr, Rot& R, bool derivs)
+/* viso.cpp:1406-1424: the rotation (and its derivatives) from the six trigonometric values */
+__device__ __forceinline__ void rot_from_sincos(double sx, double cx, double sy, double cy, double sz, double cz,
+                                                const double* tr, Rot& R, bool derivs)
 {
-    const double rx = tr[0], ry = tr[1], rz = tr[2];
     R.tx = tr[3]; R.ty = tr[4]; R.tz = tr[5];
-    const double sx = viso_sc::sin_glibc(rx), cx = viso_sc::cos_glibc(rx), sy = viso_sc::sin_glibc(ry);
-    const double cy = viso_sc::cos_glibc(ry), sz = viso_sc::sin_glibc(rz), cz = viso_sc::cos_glibc(rz);
     R.r00 = +cy * cz;                R.r01 = -cy * sz;                R.r02 = +sy;
     R.r10 = +sx * sy * cz + cx * sz; R.r11 = -sx * sy * sz + cx * cz; R.r12 = -sx * cy;
     R.r20 = -cx * sy * cz + sx * sz; R.r21 = +cx * sy * sz + sx * cz; R.r22 = +cx * cy;
@@ -43,6 +42,14 @@ __device__ __forceinline__ void make_rot(const double* tr, Rot& R, bool derivs)
         R.rdrz10 = -sx * sy * sz + cx * cz; R.rdrz11 = -sx * sy * cz - cx * sz;
         R.rdrz20 = +cx * sy * sz + sx * cz; R.rdrz21 = +cx * sy * cz - sx * sz;
     }
+}
+
+__device__ __forceinline__ void make_rot(const double* tr, Rot& R, bool derivs)
+{
+    const double rx = tr[0], ry = tr[1], rz = tr[2];
+    const double sx = viso_sc::sin_glibc(rx), cx = viso_sc::cos_glibc(rx), sy = viso_sc::sin_glibc(ry);
+    const double cy = viso_sc::cos_glibc(ry), sz = viso_sc::sin_glibc(rz), cz = viso_sc::cos_glibc(rz);
+    rot_from_sincos(sx, cx, sy, cy, sz, cz, tr, R, derivs);
 }
 
 /* prediction of one point, viso.cpp:1441-1443, 1452, 1486-1489 */
@@ -71,48 +78,75 @@ __device__ __forceinline__ bool inlier_point(const Rot& R, const ParamDev& P, co
     return err2 < P.thr2;
 }
 
-/* Jacobian rows + weighted residuals of one point, viso.cpp:1441-1495 (literal; no shortcuts for the constant
- * derivative columns so that non-finite inputs propagate exactly as in the reference).
- * out: 4 rows x 7 (6 Jacobian columns + residual). */
+/* a point in the two camera frames, viso.cpp:1441-1445 */
+struct CamPt { double X1c, Y1c, Z1c, X2c; };
+__device__ __forceinline__ CamPt cam_point(const Rot& R, const ParamDev& P, double X1p, double Y1p, double Z1p)
+{
+    CamPt c;
+    c.X1c = R.r00 * X1p + R.r01 * Y1p + R.r02 * Z1p + R.tx;
+    c.Y1c = R.r10 * X1p + R.r11 * Y1p + R.r12 * Z1p + R.ty;
+    c.Z1c = R.r20 * X1p + R.r21 * Y1p + R.r22 * Z1p + R.tz;
+    c.X2c = c.X1c - P.base;
+    return c;
+}
+
+/* column j (0..5) of the four Jacobian rows of one point, viso.cpp:1455-1484 (literal; no shortcuts for the constant
+ * derivative columns so that non-finite inputs propagate exactly as in the reference) */
+__device__ __forceinline__ void jac_column(const Rot& R, const ParamDev& P, const CamPt& c, double X1p, double Y1p,
+                                           double Z1p, double weight, int j, double col[4])
+{
+    double X1cd, Y1cd, Z1cd;
+    switch (j) {
+    case 0: X1cd = 0;
+        Y1cd = R.rdrx10 * X1p + R.rdrx11 * Y1p + R.rdrx12 * Z1p;
+        Z1cd = R.rdrx20 * X1p + R.rdrx21 * Y1p + R.rdrx22 * Z1p;
+        break;
+    case 1: X1cd = R.rdry00 * X1p + R.rdry01 * Y1p + R.rdry02 * Z1p;
+        Y1cd = R.rdry10 * X1p + R.rdry11 * Y1p + R.rdry12 * Z1p;
+        Z1cd = R.rdry20 * X1p + R.rdry21 * Y1p + R.rdry22 * Z1p;
+        break;
+    case 2: X1cd = R.rdrz00 * X1p + R.rdrz01 * Y1p;
+        Y1cd = R.rdrz10 * X1p + R.rdrz11 * Y1p;
+        Z1cd = R.rdrz20 * X1p + R.rdrz21 * Y1p;
+        break;
+    case 3: X1cd = 1; Y1cd = 0; Z1cd = 0; break;
+    case 4: X1cd = 0; Y1cd = 1; Z1cd = 0; break;
+    default: X1cd = 0; Y1cd = 0; Z1cd = 1; break;
+    }
+    col[0] = weight * P.f * (X1cd * c.Z1c - c.X1c * Z1cd) / (c.Z1c * c.Z1c);
+    col[1] = weight * P.f * (Y1cd * c.Z1c - c.Y1c * Z1cd) / (c.Z1c * c.Z1c);
+    col[2] = weight * P.f * (X1cd * c.Z1c - c.X2c * Z1cd) / (c.Z1c * c.Z1c);
+    col[3] = weight * P.f * (Y1cd * c.Z1c - c.Y1c * Z1cd) / (c.Z1c * c.Z1c);
+}
+
+/* weighted residuals of one point (column 6 of its four rows), viso.cpp:1486-1494 */
+__device__ __forceinline__ void residual_column(const ParamDev& P, const CamPt& c, double weight, const double ob[4],
+                                                double col[4])
+{
+    double pred[4];
+    pred[0] = P.f * c.X1c / c.Z1c + P.cu;
+    pred[1] = P.f * c.Y1c / c.Z1c + P.cv;
+    pred[2] = P.f * c.X2c / c.Z1c + P.cu;
+    pred[3] = P.f * c.Y1c / c.Z1c + P.cv;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) col[r] = weight * (ob[r] - pred[r]);
+}
+
+/* Jacobian rows + weighted residuals of one point, viso.cpp:1441-1495.  out: 4 rows x 7 (6 Jacobian columns + residual). */
 __device__ __forceinline__ void point_rows(const Rot& R, const ParamDev& P, double X1p, double Y1p, double Z1p,
                                            double weight, const double ob[4], double out[4][7])
 {
-    const double X1c = R.r00 * X1p + R.r01 * Y1p + R.r02 * Z1p + R.tx;
-    const double Y1c = R.r10 * X1p + R.r11 * Y1p + R.r12 * Z1p + R.ty;
-    const double Z1c = R.r20 * X1p + R.r21 * Y1p + R.r22 * Z1p + R.tz;
-    const double X2c = X1c - P.base;
+    const CamPt c = cam_point(R, P, X1p, Y1p, Z1p);
+    double col[4];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-        double X1cd, Y1cd, Z1cd;
-        switch (j) {
-        case 0: X1cd = 0;
-            Y1cd = R.rdrx10 * X1p + R.rdrx11 * Y1p + R.rdrx12 * Z1p;
-            Z1cd = R.rdrx20 * X1p + R.rdrx21 * Y1p + R.rdrx22 * Z1p;
-            break;
-        case 1: X1cd = R.rdry00 * X1p + R.rdry01 * Y1p + R.rdry02 * Z1p;
-            Y1cd = R.rdry10 * X1p + R.rdry11 * Y1p + R.rdry12 * Z1p;
-            Z1cd = R.rdry20 * X1p + R.rdry21 * Y1p + R.rdry22 * Z1p;
-            break;
-        case 2: X1cd = R.rdrz00 * X1p + R.rdrz01 * Y1p;
-            Y1cd = R.rdrz10 * X1p + R.rdrz11 * Y1p;
-            Z1cd = R.rdrz20 * X1p + R.rdrz21 * Y1p;
-            break;
-        case 3: X1cd = 1; Y1cd = 0; Z1cd = 0; break;
-        case 4: X1cd = 0; Y1cd = 1; Z1cd = 0; break;
-        default: X1cd = 0; Y1cd = 0; Z1cd = 1; break;
-        }
-        out[0][j] = weight * P.f * (X1cd * Z1c - X1c * Z1cd) / (Z1c * Z1c);
-        out[1][j] = weight * P.f * (Y1cd * Z1c - Y1c * Z1cd) / (Z1c * Z1c);
-        out[2][j] = weight * P.f * (X1cd * Z1c - X2c * Z1cd) / (Z1c * Z1c);
-        out[3][j] = weight * P.f * (Y1cd * Z1c - Y1c * Z1cd) / (Z1c * Z1c);
-    }
-    double pred[4];
-    pred[0] = P.f * X1c / Z1c + P.cu;
-    pred[1] = P.f * Y1c / Z1c + P.cv;
-    pred[2] = P.f * X2c / Z1c + P.cu;
-    pred[3] = P.f * Y1c / Z1c + P.cv;
+        jac_column(R, P, c, X1p, Y1p, Z1p, weight, j, col);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) out[r][6] = weight * (ob[r] - pred[r]);
+        for (int r = 0; r < 4; ++r) out[r][j] = col[r];
+    }
+    residual_column(P, c, weight, ob, col);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[r][6] = col[r];
 }
 
 /* weight, viso.cpp:1449: read from observe column i (the LOOP index, not active[i]) */
@@ -206,7 +240,8 @@ __constant__ int c_pair_b[27] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3,
  *               to cv::mulTransposed / J^T r);
  *   lane 0      the LU solve and the convergence test (viso.cpp:1602-1617), broadcast by shuffle.
  */
-__global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4, VISO_HYP_MINB) ransac_hyp_kernel(const RansacProb* __restrict__ probs, ParamDev P)
+__global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4, VISO_HYP_MINB)
+ransac_hyp_kernel(const RansacProb* __restrict__ probs, ParamDev P, int it_cap, int* __restrict__ strag, int strag_cap)
 {
     __shared__ double rows_s[VISO_HYP_PER_CTA][12][7];
     __shared__ double sums_s[VISO_HYP_PER_CTA][28];
@@ -235,8 +270,9 @@ __global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4, VISO_HYP_MINB) ransac_hy
     const double w = weight_of(P, pb.obs[min(pi, n - 1)]); /* columns 0,1,2: the LOOP index, viso.cpp:1449 */
     double tr[6] = {0, 0, 0, 0, 0, 0};
     int ok = 0;
+    bool unfinished = !bad_index; /* left the loop at the cap without a verdict */
     if (!bad_index) {
-        for (int it = 0; it < 100; ++it) {
+        for (int it = 0; it < it_cap; ++it) {
             /* make_rot, viso.cpp:1406-1424: lane 0 -> rx, lane 1 -> ry, lane 2 -> rz */
             const double ang = tr[q < 3 ? q : 0];
             const double sv = viso_sc::sin_glibc(ang), cv = viso_sc::cos_glibc(ang);
@@ -245,18 +281,7 @@ __global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4, VISO_HYP_MINB) ransac_hy
                 const double sx = __shfl_sync(qmask, sv, q0), cx = __shfl_sync(qmask, cv, q0);
                 const double sy = __shfl_sync(qmask, sv, q0 + 1), cy = __shfl_sync(qmask, cv, q0 + 1);
                 const double sz = __shfl_sync(qmask, sv, q0 + 2), cz = __shfl_sync(qmask, cv, q0 + 2);
-                R.tx = tr[3]; R.ty = tr[4]; R.tz = tr[5];
-                R.r00 = +cy * cz;                R.r01 = -cy * sz;                R.r02 = +sy;
-                R.r10 = +sx * sy * cz + cx * sz; R.r11 = -sx * sy * sz + cx * cz; R.r12 = -sx * cy;
-                R.r20 = -cx * sy * cz + sx * sz; R.r21 = +cx * sy * sz + sx * cz; R.r22 = +cx * cy;
-                R.rdrx10 = +cx * sy * cz - sx * sz; R.rdrx11 = -cx * sy * sz - sx * cz; R.rdrx12 = -cx * cy;
-                R.rdrx20 = +sx * sy * cz + cx * sz; R.rdrx21 = -sx * sy * sz + cx * cz; R.rdrx22 = -sx * cy;
-                R.rdry00 = -sy * cz;      R.rdry01 = +sy * sz;      R.rdry02 = +cy;
-                R.rdry10 = +sx * cy * cz; R.rdry11 = -sx * cy * sz; R.rdry12 = +sx * sy;
-                R.rdry20 = -cx * cy * cz; R.rdry21 = +cx * cy * sz; R.rdry22 = -cx * sy;
-                R.rdrz00 = -cy * sz;                R.rdrz01 = -cy * cz;
-                R.rdrz10 = -sx * sy * sz + cx * cz; R.rdrz11 = -sx * sy * cz - cx * sz;
-                R.rdrz20 = +cx * sy * sz + sx * cz; R.rdrz21 = +cx * sy * cz - sx * sz;
+                rot_from_sincos(sx, cx, sy, cy, sz, cz, tr, R, true);
             }
             if (q < 3) {
                 double rows[4][7];
@@ -301,8 +326,8 @@ __global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4, VISO_HYP_MINB) ransac_hy
                 }
             }
             flag = __shfl_sync(qmask, flag, q0);
-            if (flag == 2) { ok = 0; break; }
-            if (flag == 1) { ok = 1; break; }
+            if (flag == 2) { ok = 0; unfinished = false; break; }
+            if (flag == 1) { ok = 1; unfinished = false; break; }
 #pragma unroll
             for (int j = 0; j < 6; ++j) tr[j] = tr[j] + __shfl_sync(qmask, p[j], q0);
             __syncwarp(qmask); /* rows_s / sums_s are rewritten by the next iteration */
@@ -313,6 +338,120 @@ __global__ void __launch_bounds__(VISO_HYP_PER_CTA * 4, VISO_HYP_MINB) ransac_hy
         for (int j = 0; j < 6; ++j) pb.hyp_tr[6 * hId + j] = tr[j];
         pb.hyp_ok[hId] = ok;
         pb.hyp_count[hId] = -1;
+        if (unfinished && it_cap < 100) { /* ransac_hyp_cont_kernel takes it from here (tr after it_cap iterations) */
+            const int slot = atomicAdd(strag, 1);
+            if (slot < strag_cap) { strag[2 + 2 * slot] = blockIdx.y; strag[3 + 2 * slot] = hId; }
+        }
+    }
+}
+
+/*
+ * The hypotheses ransac_hyp_kernel left unfinished at its iteration cap, ONE WARP each, iterations it0 .. 99.
+ *
+ * Why: 0.8 % of the three-point samples never converge and run all 100 iterations (viso.cpp:1590), 4.5 % need more than
+ * 8 (median 4).  A quad executes ~3600 instructions per iteration whatever its neighbours do, so the 100-iteration
+ * tail alone lasted ~0.8 ms (at 7 % warp occupancy) and set the duration of the launch.  Here the same operations are
+ * spread over a warp instead of a quad -- nothing is re-associated, every value is computed by the expression the quad
+ * kernel uses:
+ *   lanes 0..2    sin and cos of one angle each, broadcast;
+ *   lanes 0..17   (sample point, parameter j): column j of the point's four Jacobian rows (3 divisions per lane
+ *                 instead of 28);
+ *   lanes 18..20  the residual column of one point each;
+ *   lanes 0..26   one normal-equation sum each, sequentially over rows 0..11;
+ *   lane 0        the LU solve and the convergence test, broadcast.
+ * The straggler list is (problem, hypothesis) pairs; the state is hyp_tr (tr after it0 iterations).
+ */
+#ifndef VISO_CONT_WARPS
+#define VISO_CONT_WARPS 2
+#endif
+__global__ void __launch_bounds__(VISO_CONT_WARPS * 32)
+ransac_hyp_cont_kernel(const RansacProb* __restrict__ probs, ParamDev P, int it0, const int* __restrict__ strag, int strag_cap)
+{
+    __shared__ double rows_s[VISO_CONT_WARPS][12][7];
+    __shared__ double sums_s[VISO_CONT_WARPS][28];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int count = min(strag[0], strag_cap);
+    for (int e = blockIdx.x * VISO_CONT_WARPS + w; e < count; e += gridDim.x * VISO_CONT_WARPS) {
+        const RansacProb& pb = probs[strag[2 + 2 * e]];
+        const int hId = strag[3 + 2 * e];
+        const int n = *pb.n;
+        int s[3];
+        if (pb.table) { s[0] = pb.table[3 * hId]; s[1] = pb.table[3 * hId + 1]; s[2] = pb.table[3 * hId + 2]; }
+        else sample_from_seeds(pb.seeds + 3 * hId, n, s);
+        const int S = pb.stride;
+        /* this lane's sample point: (point, column) for lanes 0..17, the point of the residual column for 18..20 */
+        const int pi = lane < 18 ? lane / 6 : (lane < 21 ? lane - 18 : 0);
+        const int jc = lane < 18 ? lane - 6 * pi : 6;
+        const int a = s[pi]; /* in range: the quad kernel only lists hypotheses with valid samples */
+        const double Xp = pb.X[a], Yp = pb.X[S + a], Zp = pb.X[2 * S + a];
+        double ob[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ob[r] = pb.obs[r * S + a];
+        const double wgt = weight_of(P, pb.obs[min(pi, n - 1)]); /* columns 0,1,2: the LOOP index, viso.cpp:1449 */
+        double tr[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) tr[j] = pb.hyp_tr[6 * hId + j];
+        int ok = 0;
+        for (int it = it0; it < 100; ++it) {
+            const double ang = tr[lane < 3 ? lane : 0];
+            const double sv = viso_sc::sin_glibc(ang), cv = viso_sc::cos_glibc(ang);
+            Rot R;
+            {
+                const double sx = __shfl_sync(FULL, sv, 0), cx = __shfl_sync(FULL, cv, 0);
+                const double sy = __shfl_sync(FULL, sv, 1), cy = __shfl_sync(FULL, cv, 1);
+                const double sz = __shfl_sync(FULL, sv, 2), cz = __shfl_sync(FULL, cv, 2);
+                rot_from_sincos(sx, cx, sy, cy, sz, cz, tr, R, true);
+            }
+            if (lane < 21) {
+                const CamPt c = cam_point(R, P, Xp, Yp, Zp);
+                double col[4];
+                if (lane < 18) jac_column(R, P, c, Xp, Yp, Zp, wgt, jc, col);
+                else residual_column(P, c, wgt, ob, col);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) rows_s[w][4 * pi + r][jc] = col[r];
+            }
+            __syncwarp();
+            if (lane < 27) {
+                const int sa = c_pair_a[lane], sb = c_pair_b[lane];
+                double acc = 0;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) acc += rows_s[w][k][sa] * rows_s[w][k][sb];
+                sums_s[w][lane] = acc;
+            }
+            __syncwarp();
+            int flag = 0; /* 0 continue, 1 converged, 2 singular */
+            double p[6] = {0, 0, 0, 0, 0, 0};
+            if (lane == 0) {
+                double A[6][6], b[6];
+                int t = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int c = r; c < 6; ++c) { A[r][c] = sums_s[w][t]; A[c][r] = sums_s[w][t]; ++t; }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) b[r] = sums_s[w][21 + r];
+                if (!lu_solve6(A, b)) flag = 2;
+                else {
+                    flag = 1;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j)
+                        if (b[j] > P.thresh) flag = 0; /* fabs(p > thresh), viso.cpp:1610 */
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) p[j] = b[j];
+                }
+            }
+            flag = __shfl_sync(FULL, flag, 0);
+            if (flag == 2) { ok = 0; break; }
+            if (flag == 1) { ok = 1; break; }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) tr[j] = tr[j] + __shfl_sync(FULL, p[j], 0);
+            __syncwarp(); /* rows_s / sums_s are rewritten by the next iteration */
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) pb.hyp_tr[6 * hId + j] = tr[j];
+            pb.hyp_ok[hId] = ok;
+        }
     }
 }
 
@@ -584,13 +723,32 @@ __global__ void __launch_bounds__(256) inliers_kernel(const double* X, const dou
 
 /* ------------------------------------------------------------------------------------------------ launchers */
 
-cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, int max_n, ParamDev p, cudaStream_t s,
-                               int* launches)
+cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, int max_n, ParamDev p, int* strag,
+                               int hyp_it_cap, int sm_count, cudaStream_t s, int* launches)
 {
     if (n_probs <= 0 || max_H <= 0) return cudaSuccess;
-    ransac_hyp_kernel<<<dim3((max_H + VISO_HYP_PER_CTA - 1) / VISO_HYP_PER_CTA, n_probs), VISO_HYP_PER_CTA * 4, 0, s>>>(probs, p);
-    cudaError_t e = cudaGetLastError();
+    const int it_cap = strag ? std::max(1, std::min(100, hyp_it_cap)) : 100;
+    const long long strag_cap = (long long)n_probs * max_H;
+    cudaError_t e;
+    if (it_cap < 100) {
+        e = viso_launch_zero(strag, 1, s);
+        if (e != cudaSuccess) return e;
+        if (launches) *launches += 1;
+    }
+    ransac_hyp_kernel<<<dim3((max_H + VISO_HYP_PER_CTA - 1) / VISO_HYP_PER_CTA, n_probs), VISO_HYP_PER_CTA * 4, 0, s>>>(
+        probs, p, it_cap, strag, (int)strag_cap);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (it_cap < 100) {
+        /* one warp per unfinished hypothesis where they fit (their number is only known on the device: a grid-stride
+         * loop over the list takes whatever is there) */
+        const long long want = (strag_cap + VISO_CONT_WARPS - 1) / VISO_CONT_WARPS;
+        const int grid = (int)std::max(1LL, std::min(want, (long long)std::max(1, sm_count) * (16 / VISO_CONT_WARPS)));
+        ransac_hyp_cont_kernel<<<grid, VISO_CONT_WARPS * 32, 0, s>>>(probs, p, it_cap, strag, (int)strag_cap);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (launches) *launches += 1;
+    }
     ransac_score_kernel<<<dim3((max_H + 7) / 8, n_probs), 256, 0, s>>>(probs, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -208,8 +208,13 @@ cudaError_t viso_launch_match(const MatchJob* jobs, int n_jobs, int max_nq, int 
                               cudaStream_t s, int* launches);
 cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, int max_n, ParamDev p, cudaStream_t s);
 cudaError_t viso_launch_circle(const CircleJob* jobs, int n_jobs, cudaStream_t s);
-cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, int max_n, ParamDev p, cudaStream_t s,
-                               int* launches);
+/* strag: device scratch of 2 + 2 * n_probs * max_H ints (count, pad, then (problem, hypothesis) pairs) for the hypotheses
+ * the quad kernel hands over to the warp-per-hypothesis kernel after hyp_it_cap iterations; null or a cap of 100 =
+ * everything in the quad kernel */
+#define VISO_HYP_IT_CAP 8 /* iterations in the quad kernel before a hypothesis is handed to the warp-per-hypothesis one:
+                             93 % of the samples have converged by then; 6, 8 and 12 measure the same */
+cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, int max_n, ParamDev p, int* strag,
+                               int hyp_it_cap, int sm_count, cudaStream_t s, int* launches);
 cudaError_t viso_launch_gn(const double* X, const double* obs, int stride, const int* active, int na, double* tr,
                            int* ok, double* scratch, ParamDev p, cudaStream_t s);
 cudaError_t viso_launch_inliers(const double* X, const double* obs, int n, int stride, const double* tr, int* inliers,

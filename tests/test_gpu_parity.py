@@ -358,6 +358,32 @@ def test_ransac_minimize_reproj(ctx, api, oracle, n, H):
     assert np.abs(g["tr"] - tr_true).max() < 0.05
 
 
+def test_ransac_hypotheses_do_not_depend_on_the_iteration_cap(ctx, api, oracle):
+    """viso_set_hyp_iteration_cap: where a hypothesis moves from the quad kernel to the warp-per-hypothesis kernel changes
+    which lanes compute what, never the values -- every output, including the tr of the hypotheses that fail after 100
+    iterations, is bit-identical for every cap, and equal to the oracle"""
+    from libviso_b200 import synth
+    n, H = 400, 3000
+    X, obs, _ = synth.make_ransac_problem(n, seed=77, outlier_frac=0.3)
+    pg, po = _params(api, oracle, H)
+    table = oracle.randomsample_table(99, H, n)
+    o = oracle.ransac_minimize_reproj(X, obs, po, table)
+    try:
+        ctx.set_hyp_iteration_cap(100)
+        ref = ctx.ransac_minimize_reproj(X, obs, pg, table)
+        assert np.array_equal(ref["hyp_ok"], o["hyp_ok"]) and np.array_equal(ref["hyp_count"], o["hyp_count"])
+        assert (o["hyp_ok"] == 0).sum() >= 10            # there ARE hypotheses that run out of iterations
+        for cap in (1, 2, 5, 8, 30, 99):
+            ctx.set_hyp_iteration_cap(cap)
+            g = ctx.ransac_minimize_reproj(X, obs, pg, table)
+            for k in ("hyp_ok", "hyp_count", "inliers"):
+                assert np.array_equal(g[k], ref[k]), (cap, k)
+            assert np.array_equal(g["hyp_tr"].view(np.int64), ref["hyp_tr"].view(np.int64)), cap
+            assert g["best_hyp"] == ref["best_hyp"] and np.array_equal(g["tr"].view(np.int64), ref["tr"].view(np.int64))
+    finally:
+        ctx.set_hyp_iteration_cap(8)
+
+
 def test_ransac_zero_iterations(ctx, api, oracle):
     """param.ransac_iter == 0: the loop of viso.cpp:1555 never runs -> false, best_tr untouched, no inliers"""
     from libviso_b200 import synth
