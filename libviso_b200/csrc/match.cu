@@ -83,7 +83,10 @@ __global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __r
 {
     constexpr int side = 2 * radius + 1, dlen = side * side, wside = side + 2;
     static_assert(wside <= 16 && dlen <= VISO_DESC_U16, "half a warp per keypoint: radius <= 6");
-    __shared__ __align__(16) unsigned short out_s[8][VISO_EXTRACT_ROUNDS][2][VISO_DESC_U16];
+    /* a staging row: the 128 packed elements, then a trash area for the lanes beyond the window (columns side..15 store
+     * there instead of branching around the store: element (r, col) of such a lane lands at 128 + (col - side) + r * side) */
+    constexpr int SROW = VISO_DESC_U16 + (16 - side) + (side - 1) * side + 1 + 7 & ~7;
+    __shared__ __align__(16) unsigned short out_s[8][VISO_EXTRACT_ROUNDS][2][SROW];
     const ExtractJob job = jobs[blockIdx.y];
     if (!*job.from_image) return;
     const int n = *job.n;
@@ -91,12 +94,13 @@ __global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __r
     const int half = lane >> 4, col = lane & 15;
     constexpr int KPW = 2 * VISO_EXTRACT_ROUNDS;
     /* the pad elements of the staging rows stay zero */
-    for (int i = lane; i < VISO_EXTRACT_ROUNDS * 2 * VISO_DESC_U16; i += 32) (&out_s[warp][0][0][0])[i] = 0;
+    for (int i = lane; i < VISO_EXTRACT_ROUNDS * 2 * SROW; i += 32) (&out_s[warp][0][0][0])[i] = 0;
     __syncwarp();
+    const int cx = min(col, wside - 1);                                   /* lanes beyond the window repeat its last column */
+    const int ocol = col < side ? col : VISO_DESC_U16 + (col - side);      /* where this lane's elements go in a staging row */
     for (int row0 = (blockIdx.x * 8 + warp) * KPW; row0 < n; row0 += gridDim.x * 8 * KPW) {
         int px[VISO_EXTRACT_ROUNDS], py[VISO_EXTRACT_ROUNDS];
-        bool interior[VISO_EXTRACT_ROUNDS];
-        unsigned char p[VISO_EXTRACT_ROUNDS][wside];
+        bool inside = true; /* every window of this warp's keypoints lies inside the image */
 #pragma unroll
         for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
             const int kr = min(row0 + 2 * q + half, n - 1);
@@ -104,32 +108,46 @@ __global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __r
             if (job.srec) { const uint4 sr = job.srec[kr]; kp = make_float2(__uint_as_float(sr.x), __uint_as_float(sr.y)); }
             else kp = job.kp[kr];
             px[q] = __float2int_rn(kp.x); py[q] = __float2int_rn(kp.y);
-            /* the whole window inside the image: no reflection, no masked sample (uniform over the half warp) */
-            interior[q] = px[q] > radius && px[q] + radius + 1 < width && py[q] > radius && py[q] + radius + 1 < height;
-            const int cx = min(col, wside - 1); /* lanes beyond the window repeat its last column */
-            if (interior[q]) {
+            inside = inside && px[q] > radius && px[q] + radius + 1 < width && py[q] > radius && py[q] + radius + 1 < height;
+        }
+        unsigned char p[VISO_EXTRACT_ROUNDS][wside];
+        if (__all_sync(FULL, inside)) {
+            /* the common case, warp uniform: no reflection, no masked sample, no branch in the element loop */
+#pragma unroll
+            for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
                 const unsigned char* base = job.img + (size_t)(py[q] - radius - 1) * pitch + (px[q] - radius - 1 + cx);
 #pragma unroll
                 for (int r = 0; r < wside; ++r) p[q][r] = __ldg(base + r * pitch);
-            } else {
+            }
+#pragma unroll
+            for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
+                unsigned short* orow = out_s[warp][q][half] + ocol;
+#pragma unroll
+                for (int r = 0; r < side; ++r) {
+                    const int sv = (int)p[q][r] + 2 * (int)p[q][r + 1] + (int)p[q][r + 2]; /* column cx, image rows y-1..y+1 */
+                    const int sob = __shfl_down_sync(FULL, sv, 2, 16) - sv;                 /* s(x+1) - s(x-1), x = px-R+col */
+                    orow[r * side] = (unsigned short)(sob + 1024);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
                 const int ix = reflect101(px[q] - radius - 1 + cx, width);
 #pragma unroll
                 for (int r = 0; r < wside; ++r)
                     p[q][r] = __ldg(job.img + (size_t)reflect101(py[q] - radius - 1 + r, height) * pitch + ix);
             }
-        }
 #pragma unroll
-        for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
-            unsigned short* orow = out_s[warp][q][half];
+            for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
+                unsigned short* orow = out_s[warp][q][half] + ocol;
 #pragma unroll
-            for (int r = 0; r < side; ++r) {
-                const int sv = (int)p[q][r] + 2 * (int)p[q][r + 1] + (int)p[q][r + 2]; /* column cx, image rows y-1..y+1 */
-                int sob = __shfl_down_sync(FULL, sv, 2, 16) - sv;                       /* s(x+1) - s(x-1), x = px-R+col */
-                if (!interior[q]) {
+                for (int r = 0; r < side; ++r) {
+                    const int sv = (int)p[q][r] + 2 * (int)p[q][r + 1] + (int)p[q][r + 2];
+                    int sob = __shfl_down_sync(FULL, sv, 2, 16) - sv;
                     const int y = py[q] + r - radius, x = px[q] + col - radius;
-                    if (!(y > 0 && y < height && x > 0 && x < width)) sob = 0;           /* viso.cpp:1018 */
+                    if (!(y > 0 && y < height && x > 0 && x < width)) sob = 0;               /* viso.cpp:1018 */
+                    orow[r * side] = (unsigned short)(sob + 1024);
                 }
-                if (col < side) orow[r * side + col] = (unsigned short)(sob + 1024);
             }
         }
         __syncwarp();
@@ -137,8 +155,8 @@ __global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __r
         for (int q = 0; q < VISO_EXTRACT_ROUNDS; ++q) {
             const int row = row0 + 2 * q + half;
             const uint4 w = reinterpret_cast<const uint4*>(out_s[warp][q][half])[col];
-            unsigned sum = (w.x & 0xffffu) + (w.x >> 16) + (w.y & 0xffffu) + (w.y >> 16) + (w.z & 0xffffu) + (w.z >> 16) +
-                           (w.w & 0xffffu) + (w.w >> 16);
+            /* sum of the eight u16 of this lane: dp2a with ones adds the two halves of a word to the accumulator */
+            unsigned sum = __dp2a_lo(w.x, 0x0101u, __dp2a_lo(w.y, 0x0101u, __dp2a_lo(w.z, 0x0101u, __dp2a_lo(w.w, 0x0101u, 0u))));
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o, 16);
             if (row < n) {
