@@ -79,7 +79,10 @@ __device__ __forceinline__ int reflect101(int i, int n)
 }
 
 template <int radius>
-__global__ void __launch_bounds__(256) extract_desc_kernel(const ExtractJob* __restrict__ jobs, int width, int height, int pitch)
+#ifndef VISO_EXTRACT_MINB
+#define VISO_EXTRACT_MINB 6 /* 40 registers, 48 warps per SM: the kernel waits on image lines from DRAM */
+#endif
+__global__ void __launch_bounds__(256, VISO_EXTRACT_MINB) extract_desc_kernel(const ExtractJob* __restrict__ jobs, int width, int height, int pitch)
 {
     constexpr int side = 2 * radius + 1, dlen = side * side, wside = side + 2;
     static_assert(wside <= 16 && dlen <= VISO_DESC_U16, "half a warp per keypoint: radius <= 6");
