@@ -27,10 +27,13 @@
 #define VISO_MATCH_WARPS 4
 #endif
 #ifndef VISO_EVAL_DEPTH
-#define VISO_EVAL_DEPTH 2          /* SAD steps whose row loads are issued together (4 rows each) */
+#define VISO_EVAL_DEPTH 1          /* SAD steps whose row loads are issued together (4 rows each); with 36 warps per SM one
+                                      step in flight per warp measures best (6.22 ms; 2: 6.27, 3 / 4: 6.27) */
 #endif
 #ifndef VISO_MATCH_MINB
-#define VISO_MATCH_MINB 8          /* resident CTAs per SM the match kernels are compiled for */
+#define VISO_MATCH_MINB 9          /* resident CTAs per SM the tile kernel is compiled for: 56 registers, 36 warps per SM.  Since
+                                      the running sums moved to the FMA pipe the kernel fits: 6.48 -> 6.27 ms (7: 6.64, 8: 6.48,
+                                      10 = 48 registers: 6.80) */
 #endif
 #ifndef VISO_TILE_W
 #define VISO_TILE_W 6            /* query tile of sad_match: 6 x 4 cells = 96 x 64 px */
