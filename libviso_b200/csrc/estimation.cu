@@ -629,7 +629,7 @@ __device__ int inliers_block(const double* __restrict__ X, const double* __restr
 
 /* One CTA per problem: viso.cpp:1564-1579 */
 #ifndef VISO_FINAL_MINB
-#define VISO_FINAL_MINB 2 /* 128 registers (spills in the row evaluation are hidden: the CTA waits on barriers and the sequential sums), -0.07 ms */
+#define VISO_FINAL_MINB 4 /* 64 registers (the spills of the row evaluation are hidden: the CTA waits on barriers and on the sequential sums); 1 -> 2 -> 4 CTAs per SM: 0.43 -> 0.36 -> 0.28 ms, 5 and more lose again */
 #endif
 __global__ void __launch_bounds__(256, VISO_FINAL_MINB) ransac_final_kernel(const RansacProb* __restrict__ probs, ParamDev P)
 {
