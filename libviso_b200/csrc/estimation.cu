@@ -629,9 +629,14 @@ __device__ int inliers_block(const double* __restrict__ X, const double* __restr
 
 /* One CTA per problem: viso.cpp:1564-1579 */
 #ifndef VISO_FINAL_MINB
-#define VISO_FINAL_MINB 4 /* 64 registers (the spills of the row evaluation are hidden: the CTA waits on barriers and on the sequential sums); 1 -> 2 -> 4 CTAs per SM: 0.43 -> 0.36 -> 0.28 ms, 5 and more lose again */
+#define VISO_FINAL_MINB 4 /* 64 registers (the spills of the row evaluation are hidden: the CTA waits on barriers and on the sequential sums); 1 -> 2 -> 4 CTAs per SM: 0.43 -> 0.28 -> 0.22 ms, 5 and more lose again */
 #endif
-__global__ void __launch_bounds__(256, VISO_FINAL_MINB) ransac_final_kernel(const RansacProb* __restrict__ probs, ParamDev P)
+/* MINB = resident CTAs per SM the instance is compiled for: VISO_FINAL_MINB (64 registers) for the pipeline's problems
+ * (max_n = keypoints per image, a few hundred correspondences, sequential sums), 1 (all the registers it wants) for
+ * problems of more than 4096 correspondences, whose parallel
+ * normal-equation sums keep 27 accumulators per thread (BASELINE configs[3]: 1.29 instead of 1.45 ms per call) */
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) ransac_final_kernel(const RansacProb* __restrict__ probs, ParamDev P)
 {
     __shared__ int warp_tot[32];
     __shared__ int best_cnt_s[256], best_idx_s[256];
@@ -752,7 +757,8 @@ cudaError_t viso_launch_ransac(const RansacProb* probs, int n_probs, int max_H, 
     ransac_score_kernel<<<dim3((max_H + 7) / 8, n_probs), 256, 0, s>>>(probs, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    ransac_final_kernel<<<n_probs, 256, 0, s>>>(probs, p);
+    if (max_n > 4 * VISO_GN_PARALLEL_MIN) ransac_final_kernel<1><<<n_probs, 256, 0, s>>>(probs, p);
+    else ransac_final_kernel<VISO_FINAL_MINB><<<n_probs, 256, 0, s>>>(probs, p);
     if (launches) *launches += 3;
     return cudaGetLastError();
 }
