@@ -58,7 +58,7 @@ def parse_args():
                     help="distinct rendered frames per sequence; the sequence drives back and forth over them (every frame "
                          "has its own HBM copy, so the working set is the full --frames)")
     ap.add_argument("--seed", type=int, default=1000, help="sequence s is rendered with seed --seed + s")
-    ap.add_argument("--cpu-pairs", type=int, default=96, help="frame pairs in the cpu_baseline sample")
+    ap.add_argument("--cpu-pairs", type=int, default=384, help="frame pairs in the cpu_baseline sample (about 16 s of CPU work; every record of the sample is compared with the GPU run)")
     ap.add_argument("--chunk", type=int, default=0,
                     help="frames per upload/compute chunk of the e2e pipeline (0: 125, or 250 with --input raw -- measured)")
     ap.add_argument("--e2e-buffers", type=int, default=2, choices=[1, 2],
