@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(const PackJob* __restric
  * is the descriptor at srec[p].xy and its sum lands in srec[p].w (job.srec == null: rows follow job.kp, sums to rsum).  The image is touched once per frame, so the loads mostly miss to DRAM: a warp issues the loads of
  * VISO_EXTRACT_ROUNDS x 2 keypoints before using any.
  */
+#ifndef VISO_EXTRACT_ITERS
+#define VISO_EXTRACT_ITERS 16 /* iterations per warp: amortises the job set-up of a CTA (1: 0.79 ms, 8 and more: 0.66 ms) */
+#endif
 #ifndef VISO_EXTRACT_ROUNDS
 #define VISO_EXTRACT_ROUNDS 2
 #endif
@@ -80,7 +83,7 @@ __device__ __forceinline__ int reflect101(int i, int n)
 
 template <int radius>
 #ifndef VISO_EXTRACT_MINB
-#define VISO_EXTRACT_MINB 6 /* 40 registers, 48 warps per SM: the kernel waits on image lines from DRAM */
+#define VISO_EXTRACT_MINB 8 /* 32 registers, 64 warps per SM: the kernel waits on image lines from DRAM */
 #endif
 __global__ void __launch_bounds__(256, VISO_EXTRACT_MINB) extract_desc_kernel(const ExtractJob* __restrict__ jobs, int width, int height, int pitch)
 {
@@ -96,8 +99,9 @@ __global__ void __launch_bounds__(256, VISO_EXTRACT_MINB) extract_desc_kernel(co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = lane >> 4, col = lane & 15;
     constexpr int KPW = 2 * VISO_EXTRACT_ROUNDS;
-    /* the pad elements of the staging rows stay zero */
-    for (int i = lane; i < VISO_EXTRACT_ROUNDS * 2 * SROW; i += 32) (&out_s[warp][0][0][0])[i] = 0;
+    /* the pad elements dlen..127 of the staging rows are zero and stay zero (nothing else ever writes them) */
+    for (int i = lane; i < VISO_EXTRACT_ROUNDS * 2 * (VISO_DESC_U16 - dlen); i += 32)
+        (&out_s[warp][0][0][0])[(i / (VISO_DESC_U16 - dlen)) * SROW + dlen + i % (VISO_DESC_U16 - dlen)] = 0;
     __syncwarp();
     const int cx = min(col, wside - 1);                                   /* lanes beyond the window repeat its last column */
     const int ocol = col < side ? col : VISO_DESC_U16 + (col - side);      /* where this lane's elements go in a staging row */
@@ -1349,7 +1353,8 @@ cudaError_t viso_launch_extract(const ExtractJob* jobs, int n_jobs, int max_n, i
                                 cudaStream_t s)
 {
     if (n_jobs <= 0 || max_n <= 0) return cudaSuccess;
-    dim3 grid((max_n + 16 * VISO_EXTRACT_ROUNDS - 1) / (16 * VISO_EXTRACT_ROUNDS), n_jobs);
+    /* VISO_EXTRACT_ITERS iterations of 2 * VISO_EXTRACT_ROUNDS keypoints per warp */
+    dim3 grid((max_n + 16 * VISO_EXTRACT_ROUNDS * VISO_EXTRACT_ITERS - 1) / (16 * VISO_EXTRACT_ROUNDS * VISO_EXTRACT_ITERS), n_jobs);
     if (radius != 5) return cudaErrorInvalidValue; /* the pipeline's descriptor radius (viso.cpp:1174) */
     extract_desc_kernel<5><<<grid, 256, 0, s>>>(jobs, width, height, pitch);
     return cudaGetLastError();
