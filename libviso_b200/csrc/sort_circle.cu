@@ -157,7 +157,10 @@ __device__ void cta_introsort_loop(viso_sort::KV* p, int n, unsigned short* posL
  * std::sort gives the Match vector.  Larger inputs are sorted in place in global memory by one thread with the
  * sequential restatement.
  */
-__global__ void __launch_bounds__(128) compact_sort_kernel(const SortJob* __restrict__ jobs, ParamDev P, int smem_cap)
+#ifndef VISO_SORT_THREADS
+#define VISO_SORT_THREADS 128
+#endif
+__global__ void __launch_bounds__(VISO_SORT_THREADS) compact_sort_kernel(const SortJob* __restrict__ jobs, ParamDev P, int smem_cap)
 {
     extern __shared__ int sort_sm[];
     __shared__ int warp_tot[32];
@@ -349,7 +352,7 @@ cudaError_t viso_launch_sort(const SortJob* jobs, int n_jobs, int max_n, ParamDe
         cudaError_t e = cudaFuncSetAttribute(compact_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    compact_sort_kernel<<<n_jobs, 128, smem, s>>>(jobs, p, cap);
+    compact_sort_kernel<<<n_jobs, VISO_SORT_THREADS, smem, s>>>(jobs, p, cap);
     return cudaGetLastError();
 }
 
