@@ -958,7 +958,10 @@ sad_match_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg 
  * radius, max_neighbors and density.  With only_pending it completes the queries the tile kernel marked
  * VISO_PENDING; VISO_MATCH_MODE=generic runs everything through it (A/B measurements and tests).
  */
-__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32)
+#ifndef VISO_GENERIC_MINB
+#define VISO_GENERIC_MINB 6 /* 80 registers: BASELINE configs[2] 0.212 / 0.309 ms (at the 96 the compiler picks unprompted) -> 0.199 / 0.271 ms */
+#endif
+__global__ void __launch_bounds__(VISO_MATCH_WARPS * 32, VISO_GENERIC_MINB)
 sad_match_generic_kernel(const MatchJob* __restrict__ jobs, MatchParamsPair mp, GridCfg g, unsigned long long* sad_pairs,
                          PendingList pend, int only_pending)
 {
