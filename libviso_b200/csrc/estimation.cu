@@ -197,6 +197,58 @@ __device__ __forceinline__ bool lu_solve6(double A[6][6], double b[6])
     return true;
 }
 
+
+/* lu_solve6 spread over a warp: lane c < 6 holds column c of A (a[r] = A[r][c]), lane 6 the right-hand side; the other
+ * lanes idle along.  Every scalar operation of lu_solve6 is performed once, by the lane that owns its result, on the same
+ * operands in the same order -- the pivot search and -1 / pivot on the pivot column's lane, alpha = A[j][i] * d there as
+ * well (broadcast), A[j][c] += alpha * A[i][c] on lane c, the back substitution on every lane alike from shuffled
+ * operands -- so the solution is bit-identical; columns left of the pivot are swapped along with the rest, which
+ * lu_solve6 does not do, but nothing reads them again.  x[6] and the return value are the same on all lanes. */
+__device__ __forceinline__ bool lu_solve6_warp(const double* sums /* [27]: upper triangle row-major, then J^T r */, int lane,
+                                               double x[6])
+{
+    const double eps = 2.220446049250313e-16 * 100;
+    double a[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        int t = 21 + r; /* lane 6 (and the idle lanes): the right-hand side */
+        if (lane < 6) {
+            const int lo = min(r, lane), hi = max(r, lane);
+            t = lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo);
+        }
+        a[r] = sums[t];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        int k = i;
+        double best = fabs(a[i]);
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) {
+            const double v = fabs(a[j]);
+            if (v > best) { best = v; k = j; }
+        }
+        k = __shfl_sync(FULL, k, i);
+        if (__shfl_sync(FULL, best < eps ? 1 : 0, i)) return false;
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j)
+            if (k == j) { const double t = a[i]; a[i] = a[j]; a[j] = t; }
+        const double d = __shfl_sync(FULL, -1 / a[i], i);
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) {
+            const double alpha = __shfl_sync(FULL, a[j] * d, i);
+            if (lane > i) a[j] += alpha * a[i];
+        }
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double sv = __shfl_sync(FULL, a[i], 6);
+#pragma unroll
+        for (int c = i + 1; c < 6; ++c) sv -= __shfl_sync(FULL, a[i], c) * x[c];
+        x[i] = sv / __shfl_sync(FULL, a[i], i);
+    }
+    return true;
+}
+
 /* NaN pivots: fabs(NaN) > best is false and best < eps is false, exactly like the reference's
  * std::abs comparisons -- the solve "succeeds" with NaN output (and viso.cpp:1610 then reports convergence). */
 
@@ -361,6 +413,9 @@ ransac_hyp_kernel(const RansacProb* __restrict__ probs, ParamDev P, int it_cap, 
  *   lane 0        the LU solve and the convergence test, broadcast.
  * The straggler list is (problem, hypothesis) pairs; the state is hyp_tr (tr after it0 iterations).
  */
+#ifndef VISO_CONT_LU_WARP
+#define VISO_CONT_LU_WARP 1
+#endif
 #ifndef VISO_CONT_WARPS
 #define VISO_CONT_WARPS 2
 #endif
@@ -419,8 +474,18 @@ ransac_hyp_cont_kernel(const RansacProb* __restrict__ probs, ParamDev P, int it0
                 sums_s[w][lane] = acc;
             }
             __syncwarp();
-            int flag = 0; /* 0 continue, 1 converged, 2 singular */
+            int flag; /* 0 continue, 1 converged, 2 singular: the same on all lanes */
             double p[6] = {0, 0, 0, 0, 0, 0};
+#if VISO_CONT_LU_WARP
+            if (!lu_solve6_warp(sums_s[w], lane, p)) flag = 2;
+            else {
+                flag = 1;
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    if (p[j] > P.thresh) flag = 0; /* fabs(p > thresh), viso.cpp:1610 */
+            }
+#else
+            flag = 0;
             if (lane == 0) {
                 double A[6][6], b[6];
                 int t = 0;
@@ -440,11 +505,16 @@ ransac_hyp_cont_kernel(const RansacProb* __restrict__ probs, ParamDev P, int it0
                     for (int j = 0; j < 6; ++j) p[j] = b[j];
                 }
             }
+#endif
+#if !VISO_CONT_LU_WARP
             flag = __shfl_sync(FULL, flag, 0);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) p[j] = __shfl_sync(FULL, p[j], 0);
+#endif
             if (flag == 2) { ok = 0; break; }
             if (flag == 1) { ok = 1; break; }
 #pragma unroll
-            for (int j = 0; j < 6; ++j) tr[j] = tr[j] + __shfl_sync(FULL, p[j], 0);
+            for (int j = 0; j < 6; ++j) tr[j] = tr[j] + p[j];
             __syncwarp(); /* rows_s / sums_s are rewritten by the next iteration */
         }
         if (lane == 0) {
