@@ -644,30 +644,24 @@ __device__ int gn_block(const double* __restrict__ X, const double* __restrict__
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            double A[6][6], b[6];
-            int t = 0;
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-                for (int c = a; c < 6; ++c) { A[a][c] = sums_s[t]; A[c][a] = sums_s[t]; ++t; }
-#pragma unroll
-            for (int a = 0; a < 6; ++a) b[a] = sums_s[21 + a];
+        if (threadIdx.x < 32) { /* warp 0: the LU with one column per lane (lu_solve6_warp), decision by every lane alike */
+            double b[6];
             int flag;
-            if (!lu_solve6(A, b)) flag = 2;
+            if (!lu_solve6_warp(sums_s, threadIdx.x, b)) flag = 2;
             else {
                 bool conv = true;
 #pragma unroll
                 for (int j = 0; j < 6; ++j)
                     if (b[j] > P.thresh) { conv = false; break; }
-                if (conv) flag = 1;
-                else {
-                    flag = 0;
+                flag = conv ? 1 : 0;
+            }
+            if (threadIdx.x == 0) {
+                if (flag == 0) {
 #pragma unroll
                     for (int j = 0; j < 6; ++j) tr_s[j] = tr_s[j] + b[j];
                 }
+                *flag_s = flag;
             }
-            *flag_s = flag;
         }
         __syncthreads();
         const int flag = *flag_s;
